@@ -1,0 +1,576 @@
+// C ABI of libaihab_clip.so (see include/aihab_clip.h).  Host-side orchestration only: weight packing, TMA
+// descriptor construction, workspace layout, the per-layer launch sequence and Pillow's coefficient tables.
+#include "../../include/aihab_clip.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "gemm_tcgen05.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+#define CK(expr)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) {                                                                              \
+      char _b[512];                                                                                       \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return fail(_b);                                                                                    \
+    }                                                                                                     \
+  } while (0)
+// a launcher that enqueues exactly one kernel
+#define CKL(expr)     \
+  do {                \
+    CK(expr);         \
+    g_launches += 1;  \
+  } while (0)
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int device_of(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) return a.device;
+  cudaGetLastError();
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+
+int sm_count(int dev) {
+  static std::mutex mu;
+  static std::map<int, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(dev);
+  if (it != cache.end()) return it->second;
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  cache[dev] = n;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Pillow ImagingResample coefficient tables (third-party: Pillow 12.2.0, src/libImaging/Resample.c —
+// precompute_coeffs + normalize_coeffs_8bpc; restated from the published algorithm).  One axis.
+struct AxisTable {
+  std::vector<int> bounds;  // {xmin, count} per output index
+  std::vector<int> coeffs;  // [out, ksize], 22-bit fixed point
+  int ksize = 0;
+};
+
+double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+AxisTable build_resample_axis(int in_size, int out_size) {
+  AxisTable t;
+  const double scale = static_cast<double>(in_size) / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  t.ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  t.bounds.assign(static_cast<size_t>(out_size) * 2, 0);
+  t.coeffs.assign(static_cast<size_t>(out_size) * t.ksize, 0);
+  std::vector<double> k(t.ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    const double ss = 1.0 / filterscale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = bicubic_filter((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x) {
+      if (ww != 0.0) k[x] /= ww;
+    }
+    for (int x = 0; x < xmax; ++x) {
+      const double v = k[x] * (1 << 22);
+      t.coeffs[static_cast<size_t>(xx) * t.ksize + x] = static_cast<int>(v < 0 ? -0.5 + v : 0.5 + v);
+    }
+    t.bounds[2 * xx] = xmin;
+    t.bounds[2 * xx + 1] = xmax;
+  }
+  return t;
+}
+
+struct DeviceTables {
+  int* h_bounds = nullptr;
+  int* h_coeffs = nullptr;
+  int* v_bounds = nullptr;
+  int* v_coeffs = nullptr;
+  aihab::ResampleTables t{};
+};
+
+std::mutex g_tab_mu;
+std::map<std::tuple<int, int, int, int>, DeviceTables> g_tables;  // (device, sh, sw, R)
+
+int upload_ints(const std::vector<int>& v, int** out) {
+  CK(cudaMalloc(out, v.size() * sizeof(int)));
+  CK(cudaMemcpy(*out, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// torchvision v2.Resize(int) output size (short side -> R, long side int(R * long / short)) and v2.CenterCrop
+// offsets int(round((size - R) / 2.0)); data/clip_transforms.py:51-52.
+int get_tables(int dev, int sh, int sw, int R, aihab::ResampleTables* out) {
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  auto key = std::make_tuple(dev, sh, sw, R);
+  auto it = g_tables.find(key);
+  if (it == g_tables.end()) {
+    int new_h, new_w;
+    if (sw <= sh) {
+      new_w = R;
+      new_h = static_cast<int>(static_cast<double>(R) * sh / sw);
+    } else {
+      new_h = R;
+      new_w = static_cast<int>(static_cast<double>(R) * sw / sh);
+    }
+    if (new_h < R || new_w < R) return fail("preprocess: resized image smaller than the crop");
+    DeviceTables d;
+    AxisTable th = build_resample_axis(sw, new_w);
+    AxisTable tv = build_resample_axis(sh, new_h);
+    if (upload_ints(th.bounds, &d.h_bounds) || upload_ints(th.coeffs, &d.h_coeffs) ||
+        upload_ints(tv.bounds, &d.v_bounds) || upload_ints(tv.coeffs, &d.v_coeffs))
+      return 1;
+    d.t.h_bounds = d.h_bounds;
+    d.t.h_coeffs = d.h_coeffs;
+    d.t.h_ksize = th.ksize;
+    d.t.v_bounds = d.v_bounds;
+    d.t.v_coeffs = d.v_coeffs;
+    d.t.v_ksize = tv.ksize;
+    d.t.new_w = new_w;
+    d.t.new_h = new_h;
+    d.t.crop_top = static_cast<int>(std::nearbyint((new_h - R) / 2.0));   // Python round(): half to even
+    d.t.crop_left = static_cast<int>(std::nearbyint((new_w - R) / 2.0));
+    d.t.need_h = (new_w != sw);
+    d.t.need_v = (new_h != sh);
+    it = g_tables.emplace(key, d).first;
+  }
+  *out = it->second.t;
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ handle
+struct aihab_vit {
+  aihab_vit_config cfg{};
+  int device = 0;
+  int num_sms = 148;
+  int g = 0, g2 = 0, L = 0, D = 0, Kp = 0, Kpad = 0;
+  int bf16 = 0;
+  size_t cap_rows = 0;  // max_batch * L
+
+  // packed weights (16-bit, [N, K] K-major) and fp32 vectors
+  struct Block {
+    void *w_in = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
+    float *b_in = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
+    float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    CUtensorMap m_in[2], m_out[2], m_fc[2], m_proj[2];  // [0] = 128-row box, [1] = 256-row box
+  };
+  std::vector<Block> blocks;
+  void* w_conv = nullptr;
+  CUtensorMap m_conv[2];
+  float *pos = nullptr, *cls0 = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
+        *lnpost_b = nullptr;
+
+  // workspace
+  void* patches = nullptr;  // [max_batch*g2, Kpad] 16-bit
+  float* x = nullptr;       // [cap_rows, D] fp32 residual stream
+  void* y = nullptr;        // [cap_rows, D] 16-bit (LN output / attention output)
+  void* big = nullptr;      // [cap_rows, 4D] 16-bit (qkv [.,3D] and MLP hidden [.,4D] share it)
+  CUtensorMap m_patches, m_y, m_h;
+  size_t ws_bytes = 0;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+int dev_alloc(aihab_vit* h, void** p, size_t bytes) {
+  CK(cudaMalloc(p, bytes));
+  h->allocs.push_back(*p);
+  h->ws_bytes += bytes;
+  return 0;
+}
+
+// copy an fp32 tensor (host or device) to a new device buffer
+int upload_f32(aihab_vit* h, const float* src, size_t n, float** out) {
+  if (src == nullptr) return fail("aihab_vit_create: null weight pointer");
+  if (dev_alloc(h, reinterpret_cast<void**>(out), n * sizeof(float))) return 1;
+  CK(cudaMemcpy(*out, src, n * sizeof(float), cudaMemcpyDefault));
+  return 0;
+}
+
+// fp32 [rows, cols] (host or device) -> 16-bit [rows, cols_pad] device
+int upload_16(aihab_vit* h, const float* src, int rows, int cols, int cols_pad, void** out) {
+  if (src == nullptr) return fail("aihab_vit_create: null weight pointer");
+  float* tmp = nullptr;
+  const size_t n = static_cast<size_t>(rows) * cols;
+  CK(cudaMalloc(&tmp, n * sizeof(float)));
+  cudaError_t e = cudaMemcpy(tmp, src, n * sizeof(float), cudaMemcpyDefault);
+  if (e == cudaSuccess) {
+    if (dev_alloc(h, out, static_cast<size_t>(rows) * cols_pad * 2)) {
+      cudaFree(tmp);
+      return 1;
+    }
+    e = aihab::launch_cast_pad(tmp, rows, cols, *out, cols_pad, h->bf16, 0);
+    g_launches += 1;
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  }
+  cudaFree(tmp);
+  CK(e);
+  return 0;
+}
+
+int weight_maps(aihab_vit* h, const void* w, int N, int K, CUtensorMap (&m)[2]) {
+  CK(aihab::make_tmap_2d_16bit(&m[0], w, N, K, static_cast<uint64_t>(K) * 2, 128, h->bf16));
+  CK(aihab::make_tmap_2d_16bit(&m[1], w, N, K, static_cast<uint64_t>(K) * 2, 256, h->bf16));
+  return 0;
+}
+
+int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], int M, int N, int K, int epi,
+             const float* bias, void* out16, float* out32, int ldo, cudaStream_t s) {
+  aihab::GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.ab_format = h->bf16;
+  p.epilogue = epi;
+  p.bias = bias;
+  p.out16 = out16;
+  p.out32 = out32;
+  p.ldo = ldo;
+  p.pos = h->pos;
+  p.g2 = h->g2;
+  p.scale = 1.0f;
+  p.reverse_m = 0;
+  const int bn = aihab::gemm_block_n(M, N, h->num_sms);
+  CKL(aihab::launch_gemm(ma, mw[bn == 256 ? 1 : 0], p, bn, h->num_sms, s));
+  return 0;
+}
+
+// transformer stack + ln_post on a chunk of n images whose patch rows are already in h->patches
+int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t s) {
+  const int D = h->D, L = h->L, M = n * L;
+  // conv1 as GEMM + positional embedding (clip/model.py:217-221)
+  if (run_gemm(h, h->m_patches, h->m_conv, n * h->g2, D, h->Kpad, aihab::EPI_PATCH_32, nullptr, nullptr, h->x, D, s))
+    return 1;
+  // class token row + ln_pre, in place on the fp32 residual stream (clip/model.py:220-222)
+  CKL(aihab::launch_layernorm(h->x, D, h->cls0, L, h->lnpre_g, h->lnpre_b, h->x, nullptr, 0, M, D, s));
+  for (auto& b : h->blocks) {
+    // x = x + out_proj(attn(in_proj(ln_1(x))))   (clip/model.py:181,184)
+    CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln1_g, b.ln1_b, nullptr, h->y, h->bf16, M, D, s));
+    if (run_gemm(h, h->m_y, b.m_in, M, 3 * D, D, aihab::EPI_BIAS_16, b.b_in, h->big, nullptr, 3 * D, s)) return 1;
+    CKL(aihab::launch_attention(h->big, h->y, n, L, h->cfg.heads, h->bf16, s));
+    if (run_gemm(h, h->m_y, b.m_out, M, D, D, aihab::EPI_BIAS_RES_32, b.b_out, nullptr, h->x, D, s)) return 1;
+    // x = x + c_proj(quickgelu(c_fc(ln_2(x))))   (clip/model.py:171-175,185)
+    CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln2_g, b.ln2_b, nullptr, h->y, h->bf16, M, D, s));
+    if (run_gemm(h, h->m_y, b.m_fc, M, 4 * D, D, aihab::EPI_BIAS_GELU_16, b.b_fc, h->big, nullptr, 4 * D, s))
+      return 1;
+    if (run_gemm(h, h->m_h, b.m_proj, M, D, 4 * D, aihab::EPI_BIAS_RES_32, b.b_proj, nullptr, h->x, D, s)) return 1;
+  }
+  // ln_post on token 0 of every image (clip/model.py:228); rows are L*D apart
+  float* o32 = out_dtype == AIHAB_F32 ? static_cast<float*>(feats_out) : nullptr;
+  void* o16 = out_dtype == AIHAB_F32 ? nullptr : feats_out;
+  CKL(aihab::launch_layernorm(h->x, static_cast<size_t>(L) * D, nullptr, 0, h->lnpost_g, h->lnpost_b, o32, o16,
+                              out_dtype == AIHAB_BF16, n, D, s));
+  return 0;
+}
+
+size_t dtype_size(int dt) { return dt == AIHAB_F32 ? 4 : 2; }
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int aihab_abi_version(void) { return AIHAB_ABI_VERSION; }
+const char* aihab_last_error(void) { return g_err.c_str(); }
+uint64_t aihab_kernel_launches(void) { return g_launches.load(); }
+
+int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, int device, aihab_vit** out) {
+  if (cfg == nullptr || w == nullptr || out == nullptr) return fail("aihab_vit_create: null argument");
+  *out = nullptr;
+  if (cfg->patch_size <= 0 || cfg->image_size % cfg->patch_size != 0)
+    return fail("aihab_vit_create: image_size must be a multiple of patch_size");
+  if (cfg->width % 128 != 0 || cfg->width > 2048) return fail("aihab_vit_create: width must be a multiple of 128, <= 2048");
+  if (cfg->heads * 64 != cfg->width) return fail("aihab_vit_create: heads must equal width / 64");
+  if (cfg->dtype != AIHAB_F16 && cfg->dtype != AIHAB_BF16) return fail("aihab_vit_create: dtype must be AIHAB_F16 or AIHAB_BF16");
+  if (cfg->layers <= 0 || cfg->max_batch <= 0 || w->blocks == nullptr) return fail("aihab_vit_create: bad layers/max_batch/blocks");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail("aihab_vit_create: no CUDA device (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return fail("aihab_vit_create: bad device index");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("aihab_vit_create: device is not sm_100 (Blackwell B200) — kernels are sm_100a only");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("aihab_vit_create: cudaSetDevice failed");
+  CK(aihab::gemm_init());
+
+  aihab_vit* h = new aihab_vit();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->g = cfg->image_size / cfg->patch_size;
+  h->g2 = h->g * h->g;
+  h->L = h->g2 + 1;
+  h->D = cfg->width;
+  h->Kp = 3 * cfg->patch_size * cfg->patch_size;
+  h->Kpad = round_up(h->Kp, 64);
+  h->bf16 = cfg->dtype == AIHAB_BF16;
+  h->cap_rows = static_cast<size_t>(cfg->max_batch) * h->L;
+  const int D = h->D, L = h->L;
+
+  auto bail = [&](int) {
+    aihab_vit_destroy(h);
+    return 1;
+  };
+  if (aihab::attention_init(L) != cudaSuccess) {
+    fail("aihab_vit_create: sequence too long for the attention kernel (L <= 908)");
+    return bail(1);
+  }
+  if (upload_16(h, w->conv1_weight, D, h->Kp, h->Kpad, &h->w_conv)) return bail(1);
+  if (weight_maps(h, h->w_conv, D, h->Kpad, h->m_conv)) return bail(1);
+  if (upload_f32(h, w->positional_embedding, static_cast<size_t>(L) * D, &h->pos)) return bail(1);
+  if (upload_f32(h, w->ln_pre_weight, D, &h->lnpre_g) || upload_f32(h, w->ln_pre_bias, D, &h->lnpre_b) ||
+      upload_f32(h, w->ln_post_weight, D, &h->lnpost_g) || upload_f32(h, w->ln_post_bias, D, &h->lnpost_b))
+    return bail(1);
+  {  // cls0 = class_embedding + positional_embedding[0]  (fp32 add, clip/model.py:220-221)
+    std::vector<float> cls(D), p0(D);
+    if (cudaMemcpy(cls.data(), w->class_embedding, D * sizeof(float), cudaMemcpyDefault) != cudaSuccess ||
+        cudaMemcpy(p0.data(), w->positional_embedding, D * sizeof(float), cudaMemcpyDefault) != cudaSuccess) {
+      fail("aihab_vit_create: cannot read class/positional embedding");
+      return bail(1);
+    }
+    for (int i = 0; i < D; ++i) cls[i] += p0[i];
+    if (upload_f32(h, cls.data(), D, &h->cls0)) return bail(1);
+  }
+  h->blocks.resize(cfg->layers);
+  for (int i = 0; i < cfg->layers; ++i) {
+    const aihab_vit_block_weights& s = w->blocks[i];
+    aihab_vit::Block& b = h->blocks[i];
+    if (upload_16(h, s.in_proj_weight, 3 * D, D, D, &b.w_in) || upload_16(h, s.out_proj_weight, D, D, D, &b.w_out) ||
+        upload_16(h, s.c_fc_weight, 4 * D, D, D, &b.w_fc) || upload_16(h, s.c_proj_weight, D, 4 * D, 4 * D, &b.w_proj))
+      return bail(1);
+    if (upload_f32(h, s.in_proj_bias, 3 * D, &b.b_in) || upload_f32(h, s.out_proj_bias, D, &b.b_out) ||
+        upload_f32(h, s.c_fc_bias, 4 * D, &b.b_fc) || upload_f32(h, s.c_proj_bias, D, &b.b_proj) ||
+        upload_f32(h, s.ln_1_weight, D, &b.ln1_g) || upload_f32(h, s.ln_1_bias, D, &b.ln1_b) ||
+        upload_f32(h, s.ln_2_weight, D, &b.ln2_g) || upload_f32(h, s.ln_2_bias, D, &b.ln2_b))
+      return bail(1);
+    if (weight_maps(h, b.w_in, 3 * D, D, b.m_in) || weight_maps(h, b.w_out, D, D, b.m_out) ||
+        weight_maps(h, b.w_fc, 4 * D, D, b.m_fc) || weight_maps(h, b.w_proj, D, 4 * D, b.m_proj))
+      return bail(1);
+  }
+  // workspace
+  const size_t prow = static_cast<size_t>(cfg->max_batch) * h->g2;
+  if (dev_alloc(h, &h->patches, prow * h->Kpad * 2) ||
+      dev_alloc(h, reinterpret_cast<void**>(&h->x), h->cap_rows * D * 4) || dev_alloc(h, &h->y, h->cap_rows * D * 2) ||
+      dev_alloc(h, &h->big, h->cap_rows * 4 * D * 2))
+    return bail(1);
+  if (cudaMemset(h->patches, 0, prow * h->Kpad * 2) != cudaSuccess || cudaMemset(h->y, 0, h->cap_rows * D * 2) != cudaSuccess ||
+      cudaMemset(h->big, 0, h->cap_rows * 4 * D * 2) != cudaSuccess) {
+    fail("aihab_vit_create: cudaMemset failed");
+    return bail(1);
+  }
+  if (aihab::make_tmap_2d_16bit(&h->m_patches, h->patches, prow, h->Kpad, static_cast<uint64_t>(h->Kpad) * 2, 128, h->bf16) != cudaSuccess ||
+      aihab::make_tmap_2d_16bit(&h->m_y, h->y, h->cap_rows, D, static_cast<uint64_t>(D) * 2, 128, h->bf16) != cudaSuccess ||
+      aihab::make_tmap_2d_16bit(&h->m_h, h->big, h->cap_rows, 4 * D, static_cast<uint64_t>(4 * D) * 2, 128, h->bf16) != cudaSuccess) {
+    fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the workspace");
+    return bail(1);
+  }
+  CK(cudaDeviceSynchronize());
+  *out = h;
+  return 0;
+}
+
+void aihab_vit_destroy(aihab_vit* h) {
+  if (h == nullptr) return;
+  DeviceGuard guard(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+size_t aihab_vit_workspace_bytes(const aihab_vit* h) { return h ? h->ws_bytes : 0; }
+
+int aihab_vit_encode(aihab_vit* h, const void* images, int in_dtype, int n, void* feats_out, int out_dtype,
+                     void* stream) {
+  if (h == nullptr) return fail("aihab_vit_encode: null handle");
+  if (n < 0 || in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2) return fail("aihab_vit_encode: bad argument");
+  if (n == 0) return 0;
+  if (images == nullptr || feats_out == nullptr) return fail("aihab_vit_encode: null buffer");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int R = h->cfg.image_size;
+  const size_t img_bytes = static_cast<size_t>(3) * R * R * dtype_size(in_dtype);
+  for (int i0 = 0; i0 < n; i0 += h->cfg.max_batch) {
+    const int nb = std::min(h->cfg.max_batch, n - i0);
+    const uint8_t* src = static_cast<const uint8_t*>(images) + img_bytes * i0;
+    CKL(aihab::launch_im2col(src, in_dtype, nb, R, h->cfg.patch_size, h->Kpad, h->patches, h->bf16, s));
+    void* dst = static_cast<uint8_t*>(feats_out) + static_cast<size_t>(i0) * h->D * dtype_size(out_dtype);
+    if (run_tower(h, nb, dst, out_dtype, s)) return 1;
+  }
+  return 0;
+}
+
+int aihab_vit_encode_u8(aihab_vit* h, const uint8_t* images_u8, int n, int sh, int sw, void* feats_out,
+                        int out_dtype, void* stream) {
+  if (h == nullptr) return fail("aihab_vit_encode_u8: null handle");
+  if (n < 0 || sh <= 0 || sw <= 0 || out_dtype < 0 || out_dtype > 2) return fail("aihab_vit_encode_u8: bad argument");
+  if (n == 0) return 0;
+  if (images_u8 == nullptr || feats_out == nullptr) return fail("aihab_vit_encode_u8: null buffer");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int R = h->cfg.image_size;
+  aihab::ResampleTables t;
+  if (get_tables(h->device, sh, sw, R, &t)) return 1;
+  const size_t img_bytes = static_cast<size_t>(sh) * sw * 3;
+  for (int i0 = 0; i0 < n; i0 += h->cfg.max_batch) {
+    const int nb = std::min(h->cfg.max_batch, n - i0);
+    CK(aihab::launch_preprocess(images_u8 + img_bytes * i0, nb, sh, sw, R, t, h->patches, h->bf16 ? AIHAB_BF16 : AIHAB_F16,
+                                1, h->cfg.patch_size, h->Kpad, s));
+    g_launches += (h->Kpad > h->Kp) ? 2 : 1;
+    void* dst = static_cast<uint8_t*>(feats_out) + static_cast<size_t>(i0) * h->D * dtype_size(out_dtype);
+    if (run_tower(h, nb, dst, out_dtype, s)) return 1;
+  }
+  return 0;
+}
+
+int aihab_preprocess_u8(const uint8_t* images_u8, int n, int sh, int sw, int R, void* out, int out_dtype,
+                        void* stream) {
+  if (n < 0 || sh <= 0 || sw <= 0 || R <= 0 || out_dtype < 0 || out_dtype > 2) return fail("aihab_preprocess_u8: bad argument");
+  if (n == 0) return 0;
+  if (images_u8 == nullptr || out == nullptr) return fail("aihab_preprocess_u8: null buffer");
+  const int dev = device_of(images_u8);
+  DeviceGuard guard(dev);
+  aihab::ResampleTables t;
+  if (get_tables(dev, sh, sw, R, &t)) return 1;
+  CKL(aihab::launch_preprocess(images_u8, n, sh, sw, R, t, out, out_dtype, 0, 0, 0, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int aihab_score(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C, float scale,
+                int k, float* emb_out, float* logits_out, int64_t* topk_idx, float* topk_val, void* stream) {
+  if (n < 0 || D <= 0) return fail("aihab_score: bad argument");
+  if (n == 0) return 0;
+  if (feats == nullptr) return fail("aihab_score: null feats");
+  if (proj == nullptr) E = D;
+  if (E <= 0) return fail("aihab_score: bad embed dim");
+  if (text_w != nullptr && C <= 0) return fail("aihab_score: bad class count");
+  if (k < 0 || k > 16 || (k > 0 && (text_w == nullptr || k > C || topk_idx == nullptr))) return fail("aihab_score: bad k (0..16, <= C)");
+  const int dev = device_of(feats);
+  DeviceGuard guard(dev);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // rows per pass bounded so temporaries stay small (config 5: 1M rows x 1000 classes)
+  const int chunk = 65536;
+  float *emb_tmp = nullptr, *logit_tmp = nullptr;
+  const int rows_tmp = std::min(n, chunk);
+  if (emb_out == nullptr) CK(cudaMallocAsync(&emb_tmp, static_cast<size_t>(rows_tmp) * E * 4, s));
+  if (text_w != nullptr && logits_out == nullptr) CK(cudaMallocAsync(&logit_tmp, static_cast<size_t>(rows_tmp) * C * 4, s));
+  for (int i0 = 0; i0 < n; i0 += chunk) {
+    const int nb = std::min(chunk, n - i0);
+    const float* f = feats + static_cast<size_t>(i0) * D;
+    float* emb = emb_out ? emb_out + static_cast<size_t>(i0) * E : emb_tmp;
+    if (proj != nullptr) {
+      CKL(aihab::launch_sgemm(f, proj, emb, nb, E, D, 1.0f, s));
+      CKL(aihab::launch_l2norm(emb, emb, nb, E, 1e-12f, s));
+    } else {
+      CKL(aihab::launch_l2norm(f, emb, nb, E, 1e-12f, s));
+    }
+    if (text_w != nullptr) {
+      float* lg = logits_out ? logits_out + static_cast<size_t>(i0) * C : logit_tmp;
+      CKL(aihab::launch_sgemm(emb, text_w, lg, nb, C, E, scale, s));
+      if (k > 0)
+        CKL(aihab::launch_topk(lg, nb, C, k, topk_idx + static_cast<size_t>(i0) * k,
+                               topk_val ? topk_val + static_cast<size_t>(i0) * k : nullptr, s));
+    }
+  }
+  if (emb_tmp) CK(cudaFreeAsync(emb_tmp, s));
+  if (logit_tmp) CK(cudaFreeAsync(logit_tmp, s));
+  return 0;
+}
+
+int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype, int epilogue, const float* bias,
+                 void* out16, float* out32, int ldo, const float* pos, int g2, float scale, void* stream) {
+  if (A == nullptr || W == nullptr || M <= 0 || N <= 0 || K <= 0 || (K & 7)) return fail("aihab_gemm16: bad argument (K % 8 == 0)");
+  if (ab_dtype != AIHAB_F16 && ab_dtype != AIHAB_BF16) return fail("aihab_gemm16: ab_dtype must be AIHAB_F16 or AIHAB_BF16");
+  const int dev = device_of(A);
+  DeviceGuard guard(dev);
+  CK(aihab::gemm_init());
+  const int bf16 = ab_dtype == AIHAB_BF16;
+  const int sms = sm_count(dev);
+  const int bn = aihab::gemm_block_n(M, N, sms);
+  CUtensorMap ma, mw;
+  CK(aihab::make_tmap_2d_16bit(&ma, A, M, K, static_cast<uint64_t>(K) * 2, 128, bf16));
+  CK(aihab::make_tmap_2d_16bit(&mw, W, N, K, static_cast<uint64_t>(K) * 2, bn, bf16));
+  aihab::GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.ab_format = bf16;
+  p.epilogue = epilogue;
+  p.bias = bias;
+  p.out16 = out16;
+  p.out32 = out32;
+  p.ldo = ldo;
+  p.pos = pos;
+  p.g2 = g2;
+  p.scale = scale;
+  CKL(aihab::launch_gemm(ma, mw, p, bn, sms, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int aihab_layernorm(const float* x, int rows, int D, const float* gamma, const float* beta, float* out32,
+                    void* out16, int out16_dtype, void* stream) {
+  if (x == nullptr || gamma == nullptr || beta == nullptr || rows < 0) return fail("aihab_layernorm: bad argument");
+  DeviceGuard guard(device_of(x));
+  CKL(aihab::launch_layernorm(x, D, nullptr, 0, gamma, beta, out32, out16, out16_dtype == AIHAB_BF16, rows, D,
+                              static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int aihab_attention(const void* qkv, void* out, int n, int L, int H, int dtype, void* stream) {
+  if (qkv == nullptr || out == nullptr || n < 0) return fail("aihab_attention: bad argument");
+  if (dtype != AIHAB_F16 && dtype != AIHAB_BF16) return fail("aihab_attention: dtype must be AIHAB_F16 or AIHAB_BF16");
+  DeviceGuard guard(device_of(qkv));
+  CKL(aihab::launch_attention(qkv, out, n, L, H, dtype == AIHAB_BF16, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,188 @@
+// HBM-bound kernels of the hot path: LayerNorm, im2col, weight cast.  128-bit loads/stores, one warp per row.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace aihab {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp normalises one row of D = 128 * VPL floats held entirely in registers (two-pass statistics).
+template <int VPL>
+__global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict__ x, size_t ldx,
+                                                        const float* __restrict__ cls0, int L,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* out32, void* out16,
+                                                        int out_bf16, int rows) {
+  constexpr int D = VPL * 128;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* src = (cls0 != nullptr && (row % L) == 0) ? cls0 : x + static_cast<size_t>(row) * ldx;
+  float4 v[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) v[i] = *reinterpret_cast<const float4*>(src + (i * 32 + lane) * 4);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (out32 != nullptr) *reinterpret_cast<float4*>(out32 + static_cast<size_t>(row) * D + col) = y;
+    if (out16 != nullptr) {
+      uint2 pk;
+      pk.x = out_bf16 ? ptx::pack2<true>(y.x, y.y) : ptx::pack2<false>(y.x, y.y);
+      pk.y = out_bf16 ? ptx::pack2<true>(y.z, y.w) : ptx::pack2<false>(y.z, y.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out16) + static_cast<size_t>(row) * D + col) = pk;
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p) { return __half2float(*p); }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// Each thread writes 8 consecutive patch-row columns (one 16 B store).
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ img, int n, int R, int p, int g, int Kpad,
+                                                     uint16_t* __restrict__ out, int out_bf16) {
+  const int units_per_row = Kpad >> 3;
+  const long total = static_cast<long>(n) * g * g * units_per_row;
+  const int pp = p * p;
+  const int K = 3 * pp;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long prow = idx / units_per_row;
+    const int col0 = static_cast<int>(idx - prow * units_per_row) * 8;
+    const int im = static_cast<int>(prow / (g * g));
+    const int pi = static_cast<int>(prow - static_cast<long>(im) * g * g);
+    const int gy = pi / g, gx = pi - gy * g;
+    int c = col0 / pp;
+    int rem = col0 - c * pp;
+    int ky = rem / p;
+    int kx = rem - ky * p;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (col0 + j < K) {
+        const size_t off = ((static_cast<size_t>(im) * 3 + c) * R + (gy * p + ky)) * R + (gx * p + kx);
+        f[j] = load_as_float<T>(img + off);
+      } else {
+        f[j] = 0.f;
+      }
+      if (++kx == p) {
+        kx = 0;
+        if (++ky == p) {
+          ky = 0;
+          ++c;
+        }
+      }
+    }
+    uint4 pk;
+    if (out_bf16) {
+      pk.x = ptx::pack2<true>(f[0], f[1]);
+      pk.y = ptx::pack2<true>(f[2], f[3]);
+      pk.z = ptx::pack2<true>(f[4], f[5]);
+      pk.w = ptx::pack2<true>(f[6], f[7]);
+    } else {
+      pk.x = ptx::pack2<false>(f[0], f[1]);
+      pk.y = ptx::pack2<false>(f[2], f[3]);
+      pk.z = ptx::pack2<false>(f[4], f[5]);
+      pk.w = ptx::pack2<false>(f[6], f[7]);
+    }
+    *reinterpret_cast<uint4*>(out + prow * Kpad + col0) = pk;
+  }
+}
+
+__global__ void cast_pad_kernel(const float* __restrict__ src, int rows, int cols, uint16_t* __restrict__ dst,
+                                int cols_pad, int out_bf16) {
+  const long total = static_cast<long>(rows) * cols_pad;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / cols_pad;
+    const int c = static_cast<int>(i - r * cols_pad);
+    const float v = c < cols ? src[r * cols + c] : 0.f;
+    if (out_bf16) {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      dst[i] = *reinterpret_cast<uint16_t*>(&h);
+    } else {
+      __half h = __float2half_rn(v);
+      dst[i] = *reinterpret_cast<uint16_t*>(&h);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_layernorm(const float* x, size_t ldx, const float* cls0, int L, const float* gamma,
+                             const float* beta, float* out32, void* out16, int out_bf16, int rows, int D,
+                             cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (D % 128 != 0 || D > 2048 || (ldx & 3) != 0) return cudaErrorInvalidValue;
+  const int grid = (rows + 3) / 4;
+#define AIHAB_LN(V)                                                                                            \
+  case V:                                                                                                      \
+    layernorm_kernel<V><<<grid, 128, 0, stream>>>(x, ldx, cls0, L > 0 ? L : 1, gamma, beta, out32, out16,       \
+                                                  out_bf16, rows);                                             \
+    break;
+  switch (D / 128) {
+    AIHAB_LN(1) AIHAB_LN(2) AIHAB_LN(3) AIHAB_LN(4) AIHAB_LN(5) AIHAB_LN(6) AIHAB_LN(7) AIHAB_LN(8)
+    AIHAB_LN(9) AIHAB_LN(10) AIHAB_LN(11) AIHAB_LN(12) AIHAB_LN(13) AIHAB_LN(14) AIHAB_LN(15) AIHAB_LN(16)
+    default: return cudaErrorInvalidValue;
+  }
+#undef AIHAB_LN
+  return cudaGetLastError();
+}
+
+cudaError_t launch_im2col(const void* images, int in_dtype, int n, int R, int p, int Kpad, void* out, int out_bf16,
+                          cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (R % p != 0 || (Kpad & 7) != 0 || Kpad < 3 * p * p) return cudaErrorInvalidValue;
+  const int g = R / p;
+  const long total = static_cast<long>(n) * g * g * (Kpad / 8);
+  const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 16));
+  uint16_t* o = reinterpret_cast<uint16_t*>(out);
+  switch (in_dtype) {
+    case 0: im2col_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(images), n, R, p, g, Kpad, o, out_bf16); break;
+    case 1: im2col_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(images), n, R, p, g, Kpad, o, out_bf16); break;
+    case 2: im2col_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(images), n, R, p, g, Kpad, o, out_bf16); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cast_pad(const float* src, int rows, int cols, void* dst, int cols_pad, int out_bf16,
+                            cudaStream_t stream) {
+  const long total = static_cast<long>(rows) * cols_pad;
+  if (total <= 0) return cudaSuccess;
+  const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 32));
+  cast_pad_kernel<<<grid, 256, 0, stream>>>(src, rows, cols, reinterpret_cast<uint16_t*>(dst), cols_pad, out_bf16);
+  return cudaGetLastError();
+}
+
+}  // namespace aihab

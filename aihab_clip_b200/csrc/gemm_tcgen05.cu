@@ -1,0 +1,390 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a.  See gemm_tcgen05.cuh for the contract.
+#include "gemm_tcgen05.cuh"
+#include "ptx.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace aihab {
+
+namespace {
+
+constexpr int BM = 128;      // UMMA M (one CTA, cta_group::1): accumulator row i <-> TMEM lane i
+constexpr int BK = 64;       // 64 x 16-bit = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;   // fixed for 16-bit operands
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;  // warps 4..7 are the epilogue (warp % 4 selects the TMEM lane quadrant)
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = 4 * 32 * 128;  // per epilogue warp: 32 rows x 128 B
+  static constexpr int kBiasBytes = 2 * BN * 4;
+  static constexpr int kOffA = 0;
+  static constexpr int kOffB = kStages * kABytes;
+  static constexpr int kOffStaging = kStages * kStageBytes;
+  static constexpr int kOffBias = kOffStaging + kStagingBytes;
+  static constexpr int kOffBars = kOffBias + kBiasBytes;
+  static constexpr int kNumBars = 2 * kStages + 4;
+  static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
+  static constexpr int kTotal = kOffTmemSlot + 16;
+  static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
+};
+
+__device__ __forceinline__ float quick_gelu(float x) {
+  // x * sigmoid(1.702 x)  (clip/model.py:160-162), fp32 with ex2/rcp approximations (<= 2 ulp each)
+  return __fdividef(x, 1.0f + __expf(-1.702f * x));
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+            const GemmParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  constexpr bool kOut16 = (EPI == EPI_BIAS_16 || EPI == EPI_BIAS_GELU_16);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem + L::kOffA;
+  uint8_t* sB = smem + L::kOffB;
+  uint8_t* sStaging = smem + L::kOffStaging;
+  float* sBias = reinterpret_cast<float*>(smem + L::kOffBias);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = (p.M + BM - 1) / BM;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full_bar[i], 1);
+      ptx::mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 2 * BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint64_t pol_w = ptx::policy_evict_last();  // weights are re-read by every M block
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk = tile / n_blocks;
+        const int n_blk = tile - m_blk * n_blocks;
+        if (p.reverse_m) m_blk = m_blocks - 1 - m_blk;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          ptx::tma_load_2d(sA + stage * L::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          ptx::tma_load_2d_hint(sB + stage * L::kBBytes, &tmap_w, &full_bar[stage], kb * BK, n_blk * BN, pol_w);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(p.ab_format, BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA + stage * L::kABytes));
+          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sB + stage * L::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 B (UMMA_K x 2 B) inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            ptx::umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[as]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------ epilogue
+    const int ew = warp - EPI_WARP0;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    uint8_t* stg = sStaging + ew * (32 * 128);
+    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
+    const bool bf16 = p.ab_format != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int m_blk = tile / n_blocks;
+      const int n_blk = tile - m_blk * n_blocks;
+      if (p.reverse_m) m_blk = m_blocks - 1 - m_blk;
+      const int m0 = m_blk * BM + ew * 32;
+      const int n0 = n_blk * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+
+      float* sb = sBias + as * BN;
+      if constexpr (EPI != EPI_PATCH_32) {
+        for (int i = et; i < BN; i += 128) {
+          const int n = n0 + i;
+          sb[i] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+
+      ptx::mbar_wait(&tmem_full_bar[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+
+      if constexpr (kOut16) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld_32x32(taddr + c * 64, r0);
+          ptx::tmem_ld_32x32(taddr + c * 64 + 32, r1);
+          ptx::tmem_ld_wait();
+          uint32_t pk[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a0 = __uint_as_float(r0[2 * j]) + sb[c * 64 + 2 * j];
+            float a1 = __uint_as_float(r0[2 * j + 1]) + sb[c * 64 + 2 * j + 1];
+            float b0 = __uint_as_float(r1[2 * j]) + sb[c * 64 + 32 + 2 * j];
+            float b1 = __uint_as_float(r1[2 * j + 1]) + sb[c * 64 + 32 + 2 * j + 1];
+            if constexpr (EPI == EPI_BIAS_GELU_16) {
+              a0 = quick_gelu(a0);
+              a1 = quick_gelu(a1);
+              b0 = quick_gelu(b0);
+              b1 = quick_gelu(b1);
+            }
+            pk[j] = bf16 ? ptx::pack2<true>(a0, a1) : ptx::pack2<false>(a0, a1);
+            pk[16 + j] = bf16 ? ptx::pack2<true>(b0, b1) : ptx::pack2<false>(b0, b1);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) =
+                make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          }
+          __syncwarp();
+          const int u = lane & 7;
+          const int gcol = n0 + c * 64 + u * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + (lane >> 3);
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((u ^ (row & 7)) << 4));
+            const int grow = m0 + row;
+            if (grow < p.M && gcol < p.N) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + static_cast<size_t>(grow) * p.ldo +
+                                        gcol) = v;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 v;
+            v.x = __uint_as_float(r[4 * u]);
+            v.y = __uint_as_float(r[4 * u + 1]);
+            v.z = __uint_as_float(r[4 * u + 2]);
+            v.w = __uint_as_float(r[4 * u + 3]);
+            if constexpr (EPI == EPI_BIAS_RES_32) {
+              v.x += sb[c * 32 + 4 * u];
+              v.y += sb[c * 32 + 4 * u + 1];
+              v.z += sb[c * 32 + 4 * u + 2];
+              v.w += sb[c * 32 + 4 * u + 3];
+            } else if constexpr (EPI == EPI_SCALE_32) {
+              v.x = fmaf(v.x, p.scale, sb[c * 32 + 4 * u]);
+              v.y = fmaf(v.y, p.scale, sb[c * 32 + 4 * u + 1]);
+              v.z = fmaf(v.z, p.scale, sb[c * 32 + 4 * u + 2]);
+              v.w = fmaf(v.w, p.scale, sb[c * 32 + 4 * u + 3]);
+            }
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = v;
+          }
+          __syncwarp();
+          const int u = lane & 7;
+          const int gcol = n0 + c * 32 + u * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + (lane >> 3);
+            float4 v = *reinterpret_cast<const float4*>(stg + row * 128 + ((u ^ (row & 7)) << 4));
+            const int grow = m0 + row;
+            if (grow < p.M && gcol < p.N) {
+              if constexpr (EPI == EPI_BIAS_RES_32) {
+                float4* dst = reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(grow) * p.ldo + gcol);
+                const float4 x = *dst;
+                v.x += x.x;
+                v.y += x.y;
+                v.z += x.z;
+                v.w += x.w;
+                *dst = v;
+              } else if constexpr (EPI == EPI_PATCH_32) {
+                const int img = grow / p.g2;
+                const int pi = grow - img * p.g2;
+                const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pi) * p.N + gcol));
+                v.x += pe.x;
+                v.y += pe.y;
+                v.z += pe.z;
+                v.w += pe.w;
+                const size_t tok = static_cast<size_t>(img) * (p.g2 + 1) + 1 + pi;
+                *reinterpret_cast<float4*>(p.out32 + tok * p.ldo + gcol) = v;
+              } else {
+                *reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(grow) * p.ldo + gcol) = v;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // accumulator stage drained: hand it back to the MMA issuer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+template <int BN, int EPI>
+cudaError_t set_attr() {
+  return cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              SmemLayout<BN>::kDynamic);
+}
+
+template <int BN, int EPI>
+cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, int grid,
+                       cudaStream_t stream) {
+  gemm_kernel<BN, EPI><<<grid, NUM_THREADS, SmemLayout<BN>::kDynamic, stream>>>(ta, tw, p);
+  return cudaGetLastError();
+}
+
+template <int BN>
+cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, int grid,
+                      cudaStream_t stream) {
+  switch (p.epilogue) {
+    case EPI_BIAS_16: return launch_one<BN, EPI_BIAS_16>(ta, tw, p, grid, stream);
+    case EPI_BIAS_GELU_16: return launch_one<BN, EPI_BIAS_GELU_16>(ta, tw, p, grid, stream);
+    case EPI_BIAS_RES_32: return launch_one<BN, EPI_BIAS_RES_32>(ta, tw, p, grid, stream);
+    case EPI_PATCH_32: return launch_one<BN, EPI_PATCH_32>(ta, tw, p, grid, stream);
+    case EPI_SCALE_32: return launch_one<BN, EPI_SCALE_32>(ta, tw, p, grid, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace
+
+cudaError_t gemm_init() {
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorNotSupported;
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  cudaError_t e;
+#define AIHAB_SET(BN, EPI) \
+  if ((e = set_attr<BN, EPI>()) != cudaSuccess) return e;
+  AIHAB_SET(256, EPI_BIAS_16) AIHAB_SET(256, EPI_BIAS_GELU_16) AIHAB_SET(256, EPI_BIAS_RES_32)
+  AIHAB_SET(256, EPI_PATCH_32) AIHAB_SET(256, EPI_SCALE_32)
+  AIHAB_SET(128, EPI_BIAS_16) AIHAB_SET(128, EPI_BIAS_GELU_16) AIHAB_SET(128, EPI_BIAS_RES_32)
+  AIHAB_SET(128, EPI_PATCH_32) AIHAB_SET(128, EPI_SCALE_32)
+#undef AIHAB_SET
+  return cudaSuccess;
+}
+
+cudaError_t make_tmap_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                               uint64_t row_pitch_bytes, uint32_t box_rows, int ab_format) {
+  if (g_encode == nullptr) {
+    cudaError_t e = gemm_init();
+    if (e != cudaSuccess) return e;
+  }
+  if ((row_pitch_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || box_rows > 256)
+    return cudaErrorInvalidValue;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, ab_format ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+int gemm_block_n(int M, int N, int num_sms) {
+  if (N <= 128) return 128;
+  const long m_blocks = (M + BM - 1) / BM;
+  const long t256 = m_blocks * ((N + 255) / 256);
+  const long t128 = m_blocks * ((N + 127) / 128);
+  const long cost256 = ((t256 + num_sms - 1) / num_sms) * 256;
+  const long cost128 = ((t128 + num_sms - 1) / num_sms) * 128;
+  return cost128 < cost256 ? 128 : 256;
+}
+
+cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, const GemmParams& p, int block_n,
+                        int num_sms, cudaStream_t stream) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorInvalidValue;
+  const bool out16 = (p.epilogue == EPI_BIAS_16 || p.epilogue == EPI_BIAS_GELU_16);
+  if (out16 && ((p.N & 7) || (p.ldo & 7) || p.out16 == nullptr)) return cudaErrorInvalidValue;
+  if (!out16 && ((p.N & 3) || (p.ldo & 3) || p.out32 == nullptr)) return cudaErrorInvalidValue;
+  if (p.epilogue == EPI_PATCH_32 && (p.pos == nullptr || p.g2 <= 0)) return cudaErrorInvalidValue;
+  const int m_blocks = (p.M + BM - 1) / BM;
+  const int n_blocks = (p.N + block_n - 1) / block_n;
+  const long tiles = static_cast<long>(m_blocks) * n_blocks;
+  const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+  if (block_n == 256) return launch_bn<256>(tmap_a, tmap_w, p, grid, stream);
+  if (block_n == 128) return launch_bn<128>(tmap_a, tmap_w, p, grid, stream);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace aihab

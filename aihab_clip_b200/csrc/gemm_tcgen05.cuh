@@ -1,0 +1,57 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+//   A : activations, row-major [M, K] 16-bit (fp16 or bf16)         -> K-major UMMA operand A
+//   W : weights in the reference's nn.Linear layout [N, K] 16-bit   -> K-major UMMA operand B
+//   accumulate fp32 in TMEM; epilogue variants cover every GEMM site of the reference hot path
+//   (clip/model.py:171-175,181,184-185,217-221 ; methods/ProLIP.py:40 ; methods/utils.py:185).
+//
+// Roles (256 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+//   warp 0 (one lane)  TMA producer : cp.async.bulk.tensor 128x64 A box + BNx64 W box per stage, SWIZZLE_128B
+//   warp 1 (one lane)  MMA issuer   : 4 x tcgen05.mma (M=128, N=BN, K=16) per stage, tcgen05.commit -> barriers
+//   warp 2             TMEM allocator (2 accumulator stages x BN fp32 columns)
+//   warps 4..7         epilogue     : tcgen05.ld -> bias/activation in fp32 -> smem transpose -> 128 B coalesced
+//                                     row segments to global (optionally read-modify-write of the fp32 residual)
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aihab {
+
+enum GemmEpilogue : int {
+  EPI_BIAS_16 = 0,       // out16[m,n] = acc + bias[n]
+  EPI_BIAS_GELU_16 = 1,  // out16[m,n] = quickgelu(acc + bias[n])             clip/model.py:160-162
+  EPI_BIAS_RES_32 = 2,   // out32[m,n] += acc + bias[n]   (fp32 residual stream) clip/model.py:184-185
+  EPI_PATCH_32 = 3,      // out32[tok(m),n] = acc + pos[1 + m % g2, n]         clip/model.py:217-221
+  EPI_SCALE_32 = 4,      // out32[m,n] = scale * acc (+ bias[n] if bias)       plain fp32 store
+};
+
+struct GemmParams {
+  int M, N, K;
+  int ab_format;      // 0 = fp16 operands, 1 = bf16 operands
+  int epilogue;       // GemmEpilogue
+  const float* bias;  // [N] fp32 or nullptr
+  void* out16;        // [M, ldo] fp16/bf16
+  float* out32;       // [*, ldo] fp32
+  int ldo;            // leading dimension (elements) of the output
+  const float* pos;   // EPI_PATCH_32: positional embedding [L, N] fp32
+  int g2;             // EPI_PATCH_32: patches per image (L = g2 + 1)
+  float scale;        // EPI_SCALE_32
+  int reverse_m;      // walk M blocks from last to first (L2 reuse of the producer's freshest rows)
+};
+
+// Encodes a 2-D tiled tensor map over a row-major [rows, cols] 16-bit matrix with a {64, box_rows} box and
+// SWIZZLE_128B.  row_pitch_bytes must be a multiple of 16.  Returns cudaSuccess or an error.
+cudaError_t make_tmap_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                               uint64_t row_pitch_bytes, uint32_t box_rows, int ab_format);
+
+// Launches the GEMM.  tmap_a box = {64,128}; tmap_w box = {64,BN} with BN = gemm_block_n(N, M).
+cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, const GemmParams& p, int block_n,
+                        int num_sms, cudaStream_t stream);
+
+// Tile-N policy shared by map construction and launch.
+int gemm_block_n(int M, int N, int num_sms);
+
+cudaError_t gemm_init();  // sets max dynamic smem attributes; resolves cuTensorMapEncodeTiled
+
+}  // namespace aihab

@@ -1,0 +1,65 @@
+// Launchers for the non-GEMM kernels of the hot path (all sm_100a, all on a caller-supplied stream).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aihab {
+
+// LayerNorm over rows of D fp32 (eps 1e-5, affine, fp32 statistics; clip/model.py:151-157).
+//   x      : fp32, row r starts at x + r * ldx
+//   cls0   : optional fp32 [D]; when non-null, rows with r % L == 0 take cls0 as their input instead of x
+//            (class_embedding + positional_embedding[0], clip/model.py:220-221)
+//   out32  : optional fp32 [rows, D] (may alias x when ldx == D)
+//   out16  : optional fp16/bf16 [rows, D]
+// D must be a multiple of 128 and <= 2048.
+cudaError_t launch_layernorm(const float* x, size_t ldx, const float* cls0, int L, const float* gamma,
+                             const float* beta, float* out32, void* out16, int out_bf16, int rows, int D,
+                             cudaStream_t stream);
+
+// im2col for the stride-p patch embedding (clip/model.py:204,217): images [N,3,R,R] -> rows [N*g*g, Kpad]
+// 16-bit with column order (c, ky, kx) matching conv1.weight.reshape(D, 3*p*p); columns >= 3*p*p are zero.
+//   in_dtype: 0 = fp32, 1 = fp16, 2 = bf16
+cudaError_t launch_im2col(const void* images, int in_dtype, int n, int R, int p, int Kpad, void* out, int out_bf16,
+                          cudaStream_t stream);
+
+// Fused single-pass attention for one (image, head) per CTA: softmax(q k^T / 8) v, head dim 64, no mask
+// (clip/model.py:179-181; nn.MultiheadAttention with batch_first=False, need_weights=False).
+//   qkv : [N*L, 3*D] 16-bit, columns [0,D) = q, [D,2D) = k, [2D,3D) = v, head h at h*64
+//   out : [N*L, D] 16-bit
+cudaError_t launch_attention(const void* qkv, void* out, int n_img, int L, int H, int is_bf16, cudaStream_t stream);
+cudaError_t attention_init(int max_L);
+
+// fp32 -> 16-bit cast of a weight matrix [rows, cols] into [rows, cols_pad] (zero padded columns).
+cudaError_t launch_cast_pad(const float* src, int rows, int cols, void* dst, int cols_pad, int out_bf16,
+                            cudaStream_t stream);
+
+// ---- scoring (methods/ProLIP.py:40, methods/utils.py:183-186, aihab_utils/evaluation.py:261-273)
+// C[M,N] = alpha * A[M,K] @ B[K,N], all fp32 row-major, fp32 FMA accumulation in k order.
+cudaError_t launch_sgemm(const float* A, const float* B, float* C, int M, int N, int K, float alpha,
+                         cudaStream_t stream);
+// rows / max(||row||_2, eps)   (F.normalize, eps 1e-12); in place allowed.
+cudaError_t launch_l2norm(const float* x, float* y, int rows, int cols, float eps, cudaStream_t stream);
+// top-k per row, descending, lowest index first among exact ties (torch.topk / argmax semantics). k <= 16.
+cudaError_t launch_topk(const float* logits, int rows, int cols, int k, int64_t* idx, float* val,
+                        cudaStream_t stream);
+
+// ---- preprocessing (data/clip_transforms.py:50-56; Pillow ImagingResample fixed-point bicubic)
+struct ResampleTables {
+  // device pointers; *_bounds = {first input index, tap count} per output index; coeffs [out, ksize] int32 (2^22)
+  const int* h_bounds;
+  const int* h_coeffs;
+  int h_ksize;
+  const int* v_bounds;
+  const int* v_coeffs;
+  int v_ksize;
+  int new_w, new_h;    // resized image size before the centre crop
+  int crop_left, crop_top;
+  int need_h, need_v;  // Pillow skips a pass whose input and output sizes are equal
+};
+// u8 [N,SH,SW,3] -> normalised output.  layout: 0 = NCHW [N,3,R,R]; 1 = im2col rows [N*g*g, Kpad] (16-bit only)
+//   out_dtype: 0 = fp32, 1 = fp16, 2 = bf16
+cudaError_t launch_preprocess(const uint8_t* in, int n, int sh, int sw, int R, const ResampleTables& t, void* out,
+                              int out_dtype, int layout, int p, int Kpad, cudaStream_t stream);
+cudaError_t preprocess_init();
+
+}  // namespace aihab

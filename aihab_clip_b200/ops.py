@@ -1,0 +1,106 @@
+"""torch.Tensor front-ends of the C-ABI entry points.  PyTorch is used for device memory and streams only; every
+computation below happens inside libaihab_clip.so.  All functions require CUDA tensors and raise otherwise."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {dt}; expected float32, float16 or bfloat16") from None
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("aihab_clip_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def gemm16(a: torch.Tensor, w: torch.Tensor, epilogue: int, bias=None, out16=None, out32=None, pos=None, g2: int = 0,
+           scale: float = 1.0):
+    """D = a @ w.T with the fused epilogue `epilogue` (see _lib.EPI_*).  a [M,K], w [N,K], fp16 or bf16."""
+    _need_cuda(a, w, bias, out16, out32, pos)
+    assert a.dtype == w.dtype and a.dtype in (torch.float16, torch.bfloat16)
+    assert a.is_contiguous() and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    out = out16 if out16 is not None else out32
+    ldo = out.stride(0)
+    rc = _lib.load().aihab_gemm16(_ptr(a), _ptr(w), M, N, K, dtype_code(a.dtype), epilogue, _ptr(bias), _ptr(out16),
+                                  _ptr(out32), ldo, _ptr(pos), g2, C.c_float(scale), _stream(a.device))
+    _lib.check(rc, "aihab_gemm16")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype: torch.dtype = torch.float32):
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    rows, D = x.shape
+    out = torch.empty(rows, D, dtype=out_dtype, device=x.device)
+    o32 = out if out_dtype == torch.float32 else None
+    o16 = None if out_dtype == torch.float32 else out
+    rc = _lib.load().aihab_layernorm(_ptr(x), rows, D, _ptr(gamma), _ptr(beta), _ptr(o32), _ptr(o16),
+                                     dtype_code(out_dtype), _stream(x.device))
+    _lib.check(rc, "aihab_layernorm")
+    return out
+
+
+def attention(qkv: torch.Tensor, n: int, L: int, H: int):
+    """qkv [n*L, 3*H*64] fp16/bf16 -> [n*L, H*64]."""
+    _need_cuda(qkv)
+    assert qkv.is_contiguous() and qkv.shape == (n * L, 3 * H * 64)
+    out = torch.empty(n * L, H * 64, dtype=qkv.dtype, device=qkv.device)
+    rc = _lib.load().aihab_attention(_ptr(qkv), _ptr(out), n, L, H, dtype_code(qkv.dtype), _stream(qkv.device))
+    _lib.check(rc, "aihab_attention")
+    return out
+
+
+def preprocess_u8(images_u8: torch.Tensor, resolution: int, out_dtype: torch.dtype = torch.float32):
+    """uint8 [N,H,W,3] (CUDA) -> normalised [N,3,R,R]; GPU twin of data/clip_transforms.py:50-56."""
+    _need_cuda(images_u8)
+    assert images_u8.dtype == torch.uint8 and images_u8.dim() == 4 and images_u8.shape[-1] == 3
+    images_u8 = images_u8.contiguous()
+    n, sh, sw, _ = images_u8.shape
+    out = torch.empty(n, 3, resolution, resolution, dtype=out_dtype, device=images_u8.device)
+    rc = _lib.load().aihab_preprocess_u8(_ptr(images_u8), n, sh, sw, resolution, _ptr(out), dtype_code(out_dtype),
+                                         _stream(images_u8.device))
+    _lib.check(rc, "aihab_preprocess_u8")
+    return out
+
+
+def score(feats: torch.Tensor, proj, text_w, scale: float = 100.0, k: int = 1, want_emb: bool = True,
+          want_logits: bool = True):
+    """proj -> L2 normalise -> scale * emb @ text_w -> top-k.  Returns (emb, logits, topk_idx, topk_val); entries
+    not requested are None.  fp32 throughout (methods/ProLIP.py:40, methods/utils.py:183-186)."""
+    _need_cuda(feats, proj, text_w)
+    f = feats.float().contiguous()
+    n, D = f.shape
+    p = proj.float().contiguous() if proj is not None else None
+    E = p.shape[1] if p is not None else D
+    w = text_w.float().contiguous() if text_w is not None else None
+    Cn = w.shape[1] if w is not None else 0
+    dev = f.device
+    emb = torch.empty(n, E, dtype=torch.float32, device=dev) if want_emb else None
+    logits = torch.empty(n, Cn, dtype=torch.float32, device=dev) if (want_logits and w is not None) else None
+    idx = torch.empty(n, k, dtype=torch.int64, device=dev) if (k > 0 and w is not None) else None
+    val = torch.empty(n, k, dtype=torch.float32, device=dev) if idx is not None else None
+    rc = _lib.load().aihab_score(_ptr(f), n, D, _ptr(p), E, _ptr(w), Cn, C.c_float(scale), k if idx is not None else 0,
+                                 _ptr(emb), _ptr(logits), _ptr(idx), _ptr(val), _stream(dev))
+    _lib.check(rc, "aihab_score")
+    return emb, logits, idx, val

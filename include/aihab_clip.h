@@ -1,0 +1,148 @@
+/*
+ * aihab_clip.h — C ABI of libaihab_clip.so: the B200-native (sm_100a) implementation of the aihab-clip
+ * image-encode + zero-shot scoring hot path.
+ *
+ * The reference (WhiteGiveFive/aihab-clip) is pure Python/PyTorch and has no FFI of its own; its boundary for
+ * this path is the Python object protocol of the model returned by clip.load (clip/clip.py:89-137).  Each entry
+ * point below names the reference call it replaces.  The Python mirror of that protocol lives in
+ * aihab_clip_b200/clip/ and binds these symbols with ctypes (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success and a non-zero code on failure; aihab_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.  No C++ exception crosses the ABI.
+ *   - all data pointers are DEVICE pointers unless the parameter is documented "host or device"; the caller owns
+ *     every input/output buffer; a handle owns its packed weights and workspace.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); work is enqueued, not awaited.
+ *   - a handle must not be used from two threads at the same time.
+ */
+#ifndef AIHAB_CLIP_H_
+#define AIHAB_CLIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIHAB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define AIHAB_API __attribute__((visibility("default")))
+#else
+#define AIHAB_API
+#endif
+
+/* element types */
+enum { AIHAB_F32 = 0, AIHAB_F16 = 1, AIHAB_BF16 = 2 };
+
+/* GEMM epilogues (aihab_gemm16) */
+enum {
+  AIHAB_EPI_BIAS_16 = 0,      /* out16 = acc + bias                                  (in_proj, clip/model.py:181) */
+  AIHAB_EPI_BIAS_GELU_16 = 1, /* out16 = quickgelu(acc + bias)                       (c_fc + QuickGELU, :162,172) */
+  AIHAB_EPI_BIAS_RES_32 = 2,  /* out32 += acc + bias                                 (out_proj / c_proj + residual, :184-185) */
+  AIHAB_EPI_PATCH_32 = 3,     /* out32[token] = acc + positional_embedding           (conv1 + pos-emb, :217-221) */
+  AIHAB_EPI_SCALE_32 = 4      /* out32 = scale * acc + bias                          (plain fp32 store) */
+};
+
+typedef struct aihab_vit aihab_vit;
+
+/* Geometry of the image tower: VisionTransformer.__init__ (clip/model.py:199-214). heads = width / 64 (:267). */
+typedef struct {
+  int image_size;  /* input_resolution R            */
+  int patch_size;  /* p                              */
+  int width;       /* D, multiple of 128             */
+  int layers;      /* number of ResidualAttentionBlock */
+  int heads;       /* D / 64                         */
+  int dtype;       /* AIHAB_F16 or AIHAB_BF16: tensor-core operand / activation format (fp32 accumulate, fp32 residual) */
+  int max_batch;   /* images processed per internal chunk (sizes the workspace) */
+} aihab_vit_config;
+
+/* One ResidualAttentionBlock (clip/model.py:165-186); fp32, reference state_dict shapes; host or device. */
+typedef struct {
+  const float* ln_1_weight;     /* [D]      */
+  const float* ln_1_bias;       /* [D]      */
+  const float* in_proj_weight;  /* [3D, D]  rows ordered q, k, v */
+  const float* in_proj_bias;    /* [3D]     */
+  const float* out_proj_weight; /* [D, D]   */
+  const float* out_proj_bias;   /* [D]      */
+  const float* ln_2_weight;     /* [D]      */
+  const float* ln_2_bias;       /* [D]      */
+  const float* c_fc_weight;     /* [4D, D]  */
+  const float* c_fc_bias;       /* [4D]     */
+  const float* c_proj_weight;   /* [D, 4D]  */
+  const float* c_proj_bias;     /* [D]      */
+} aihab_vit_block_weights;
+
+/* visual.* tensors of the reference state_dict (clip/model.py:204-214); fp32; host or device. */
+typedef struct {
+  const float* conv1_weight;         /* [D, 3, p, p] (no bias) */
+  const float* class_embedding;      /* [D]                    */
+  const float* positional_embedding; /* [L, D], L = (R/p)^2+1  */
+  const float* ln_pre_weight;        /* [D] */
+  const float* ln_pre_bias;          /* [D] */
+  const float* ln_post_weight;       /* [D] */
+  const float* ln_post_bias;         /* [D] */
+  const aihab_vit_block_weights* blocks; /* [layers], host array */
+} aihab_vit_weights;
+
+/* Library / device ------------------------------------------------------------------------------------- */
+AIHAB_API int aihab_abi_version(void);
+AIHAB_API const char* aihab_last_error(void);
+/* number of kernels this library has launched in this process (all handles, all streams) */
+AIHAB_API uint64_t aihab_kernel_launches(void);
+
+/* Image tower -------------------------------------------------------------------------------------------
+ * Replaces build_model(...).visual construction + convert_weights (clip/model.py:372-433): packs the weights
+ * into 16-bit K-major tensor-core layout, builds TMA descriptors, allocates the workspace on `device`. */
+AIHAB_API int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, int device, aihab_vit** out);
+AIHAB_API void aihab_vit_destroy(aihab_vit* h);
+AIHAB_API size_t aihab_vit_workspace_bytes(const aihab_vit* h);
+
+/* Replaces CLIP.encode_image / VisionTransformer.forward (clip/model.py:216-235, 335-336).
+ *   images   : [n, 3, R, R] NCHW, element type in_dtype, already normalised (output of the preprocess)
+ *   feats_out: [n, D] PRE-projection features ln_post(x[:,0,:]) — visual.proj is NOT applied (model.py:228-235)
+ * n may exceed max_batch; the call loops over chunks. */
+AIHAB_API int aihab_vit_encode(aihab_vit* h, const void* images, int in_dtype, int n, void* feats_out, int out_dtype,
+                     void* stream);
+
+/* Same, fed by raw uint8 HWC images: the eval preprocessing of data/clip_transforms.py:50-56 is fused in front
+ * (bit-exact Pillow bicubic resize of the short side to R, centre crop, /255, CLIP mean/std).
+ *   images_u8: [n, sh, sw, 3] */
+AIHAB_API int aihab_vit_encode_u8(aihab_vit* h, const uint8_t* images_u8, int n, int sh, int sw, void* feats_out,
+                        int out_dtype, void* stream);
+
+/* Preprocessing alone.  Replaces build_clip_transforms(is_train=False) (data/clip_transforms.py:50-56) and
+ * clip._transform (clip/clip.py:74-81) for uint8 arrays.  out: [n, 3, R, R] of out_dtype. */
+AIHAB_API int aihab_preprocess_u8(const uint8_t* images_u8, int n, int sh, int sw, int R, void* out, int out_dtype,
+                        void* stream);
+
+/* Scoring --------------------------------------------------------------------------------------------------
+ * Replaces VisProjViT.forward (methods/ProLIP.py:31-41), F.normalize (methods/utils.py:184),
+ * `100. * f @ text_weights` (methods/utils.py:185) and argmax / topk (methods/utils.py:16-21,186;
+ * aihab_utils/evaluation.py:261-273), all in fp32.
+ *   feats   : [n, D] fp32 pre-projection features
+ *   proj    : [D, E] fp32 (visual.proj) or NULL to score `feats` directly (then E = D)
+ *   text_w  : [E, C] fp32 class text embeddings (columns = classes), or NULL to stop after normalisation
+ *   scale   : logit temperature (100 in the reference)
+ *   emb_out : [n, E] fp32 L2-normalised embeddings, nullable
+ *   logits_out: [n, C] fp32, nullable
+ *   topk_idx: [n, k] int64 sorted descending, lowest index first among exact ties, nullable when k == 0
+ *   topk_val: [n, k] fp32, nullable */
+AIHAB_API int aihab_score(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C, float scale,
+                int k, float* emb_out, float* logits_out, int64_t* topk_idx, float* topk_val, void* stream);
+
+/* Building blocks (exported for per-kernel parity tests; same kernels the tower uses) ---------------------- */
+/* D[M,N] = A[M,K] * W[N,K]^T with a fused epilogue; A, W 16-bit (ab_dtype), K % 8 == 0. */
+AIHAB_API int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype, int epilogue, const float* bias,
+                 void* out16, float* out32, int ldo, const float* pos, int g2, float scale, void* stream);
+/* LayerNorm rows of D fp32 (eps 1e-5) -> out32 (nullable) and/or out16 (nullable, out16_dtype). */
+AIHAB_API int aihab_layernorm(const float* x, int rows, int D, const float* gamma, const float* beta, float* out32,
+                    void* out16, int out16_dtype, void* stream);
+/* softmax(q k^T / 8) v per (image, head); qkv [n*L, 3*H*64] 16-bit -> out [n*L, H*64]. */
+AIHAB_API int aihab_attention(const void* qkv, void* out, int n, int L, int H, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIHAB_CLIP_H_ */

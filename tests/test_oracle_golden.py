@@ -1,0 +1,105 @@
+"""Pins oracle/clip_oracle.py to the reference: every oracle function is checked against outputs of the
+unmodified reference (tests/golden/reference_outputs.npz, produced by tests/golden/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from aihab_clip_b200.weights import GEOMETRIES, make_state_dict_np, state_dict_digest, synthetic_images_u8
+from oracle import clip_oracle as O
+
+CASES = {"tiny16": ("ViT-tiny/16", 0, 6, 64), "tiny14": ("ViT-tiny/14", 1, 6, 111), "b32": ("ViT-B/32", 0, 8, 439)}
+
+
+def case_inputs(tag):
+    geom, seed, n, side = CASES[tag]
+    sd = make_state_dict_np(geom, seed)
+    u8 = np.concatenate([synthetic_images_u8(n // 2, side, seed=1234),
+                         synthetic_images_u8(n - n // 2, side, seed=1234, start=n // 2, smooth=True)])
+    return GEOMETRIES[geom], sd, u8
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest()
+
+
+@pytest.mark.parametrize("tag", ["tiny16", "tiny14", "b32"])
+def test_weights_generator_is_pinned(gold, tag):
+    _, sd, _ = case_inputs(tag)
+    assert bytes.fromhex(state_dict_digest(sd)) == gold[f"{tag}_digest"].tobytes()
+
+
+@pytest.mark.parametrize("tag", ["tiny16", "tiny14", "b32"])
+def test_encode_image_and_scoring_match_reference(gold, tag):
+    geom, sd, u8 = case_inputs(tag)
+    R = geom.image_resolution
+    x = np.stack([O.clip_preprocess(im, R) for im in u8])
+    assert sha(x) == gold[f"{tag}_pre_sha"].tobytes(), "preprocessing must be bit-exact"
+    feats = O.encode_image(sd, x)
+    np.testing.assert_allclose(feats, gold[f"{tag}_feats"], atol=2e-4, rtol=0)
+    emb, logits, top3 = O.score(feats, sd["visual.proj"], gold[f"{tag}_text_w"], 100.0, 3)
+    np.testing.assert_allclose(emb, gold[f"{tag}_emb"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(logits, gold[f"{tag}_logits"], atol=5e-4, rtol=0)
+    # scoring alone, from the reference's own features: indices must be identical
+    _, logits2, top3b = O.score(gold[f"{tag}_feats"], sd["visual.proj"], gold[f"{tag}_text_w"], 100.0, 3)
+    ref = gold[f"{tag}_logits"]
+    gaps = np.abs(np.diff(np.sort(ref, axis=1)[:, ::-1][:, :4], axis=1)).min(axis=1)
+    untied = gaps > 1e-4
+    assert (top3b[untied] == gold[f"{tag}_top3"][untied]).all()
+    assert (top3b[untied, 0] == gold[f"{tag}_argmax"][untied]).all()
+
+
+@pytest.mark.parametrize("tag", ["tiny16", "b32"])
+def test_layer_trace_matches_reference(gold, tag):
+    geom, sd, u8 = case_inputs(tag)
+    x = np.stack([O.clip_preprocess(im, geom.image_resolution) for im in u8[:2]])
+    _, trace = O.encode_image(sd, x, return_layers=True)
+    ref = gold[f"{tag}_trace"]
+    got = np.stack(trace)[:, :ref.shape[1], :ref.shape[2]]
+    np.testing.assert_allclose(got, ref, atol=3e-4, rtol=0)
+
+
+@pytest.mark.parametrize("tag", ["tiny16", "tiny14", "b32"])
+def test_encode_text_and_text_head(gold, tag):
+    _, sd, _ = case_inputs(tag)
+    before, emb = O.encode_text(sd, gold[f"{tag}_tok"])
+    np.testing.assert_allclose(before, gold[f"{tag}_text_before"], atol=2e-4, rtol=0)
+    np.testing.assert_allclose(emb, gold[f"{tag}_text_emb"], atol=2e-4, rtol=0)
+    # clip_classifier with one template: column c = normalised embedding of class c's prompt (first 3 classes)
+    head = O.text_head([e[None, :] for e in emb])
+    np.testing.assert_allclose(head, gold[f"{tag}_text_w"][:, :3], atol=2e-5, rtol=0)
+    np.testing.assert_array_equal(gold[f"{tag}_texts"][:3], gold[f"{tag}_tok"])
+
+
+def test_preprocess_bit_exact_all_cases(gold, meta):
+    for (h, w, R) in meta["pre_cases"]:
+        rng = np.random.Generator(np.random.PCG64([99, h, w, R]))
+        u8 = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+        u8[1] = synthetic_images_u8(1, max(h, w), seed=5, smooth=True)[0][:h, :w]
+        y = np.stack([O.clip_preprocess(im, R) for im in u8])
+        np.testing.assert_array_equal(y[:, :, ::37, ::41], gold[f"pre_{h}x{w}_{R}_sample"])
+        assert sha(y) == gold[f"pre_{h}x{w}_{R}_sha"].tobytes(), (h, w, R)
+
+
+def test_evaluation_functions(gold, meta):
+    logits, labels = gold["ev_logits"], gold["ev_labels"]
+    for red in ("sum", "mean", "logsumexp"):
+        got = O.aggregate_logits_to_l2(logits, meta["l3_to_l2"], len(meta["l2_names"]), red)
+        np.testing.assert_allclose(got, gold[f"ev_l2_{red}"], atol=1e-5, rtol=1e-6)
+    np.testing.assert_array_equal(np.asarray(meta["l3_to_l2"])[labels], gold["ev_l2_targets"])
+    correct, idx, probs = O.top3_metrics(logits, labels)
+    assert correct == int(gold["ev_top3_correct"])
+    np.testing.assert_array_equal(idx, gold["ev_top3_idx"])
+    np.testing.assert_allclose(probs, gold["ev_top3_probs"], atol=1e-6, rtol=1e-5)
+    assert O.cls_acc(logits, labels, 1) == pytest.approx(float(gold["ev_acc1"]))
+    assert O.cls_acc(logits, labels, 3) == pytest.approx(float(gold["ev_acc3"]))
+    with pytest.raises(ValueError):
+        O.aggregate_logits_to_l2(logits[:, :5], meta["l3_to_l2"], 11)
+    with pytest.raises(ValueError):
+        O.aggregate_logits_to_l2(logits, meta["l3_to_l2"], 11, "median")
+
+
+def test_text_head_18x80_shape(gold):
+    w = gold["b32_text_w_18x80"]
+    assert w.shape == (512, 18)
+    np.testing.assert_allclose(np.linalg.norm(w, axis=0), 1.0, atol=1e-5)
