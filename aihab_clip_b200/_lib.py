@@ -39,6 +39,8 @@ SIGNATURES = {
     "aihab_abi_version": (C.c_int, []),
     "aihab_last_error": (C.c_char_p, []),
     "aihab_kernel_launches": (C.c_uint64, []),
+    "aihab_profile_enable": (C.c_int, [C.c_int]),
+    "aihab_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_int]),
     "aihab_vit_create": (C.c_int, [C.POINTER(VitConfig), C.POINTER(VitWeights), C.c_int, C.POINTER(C.c_void_p)]),
     "aihab_vit_destroy": (None, [C.c_void_p]),
     "aihab_vit_workspace_bytes": (C.c_size_t, [C.c_void_p]),
@@ -86,3 +88,18 @@ def check(rc: int, what: str) -> None:
 
 def kernel_launches() -> int:
     return int(load().aihab_kernel_launches())
+
+
+PROFILE_CLASSES = {"gemm": 0, "attention": 1, "layernorm": 2, "preprocess": 3, "score": 4}
+
+
+def profile_enable(on: bool) -> None:
+    load().aihab_profile_enable(1 if on else 0)
+
+
+def profile_read(cls: str, reset: bool = True) -> dict:
+    """{'ms': total event time, 'launches': n, 'work': algorithmic FLOPs or bytes} for one kernel class."""
+    ms, n, work = C.c_double(), C.c_uint64(), C.c_double()
+    check(load().aihab_profile_read(PROFILE_CLASSES[cls], C.byref(ms), C.byref(n), C.byref(work), 1 if reset else 0),
+          "aihab_profile_read")
+    return {"ms": ms.value, "launches": int(n.value), "work": work.value}

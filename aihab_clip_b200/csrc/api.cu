@@ -20,6 +20,46 @@ namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 
+// ---- optional per-kernel-class timing with CUDA events on the launch stream (bench.py roofline evidence)
+enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_LN = 2, PC_PRE = 3, PC_SCORE = 4, PC_COUNT = 5 };
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cls;
+  double work;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
+
+struct ProfScope {
+  bool on = false;
+  ProfRec r{};
+  cudaStream_t s;
+  ProfScope(int cls, double work, cudaStream_t stream) : s(stream) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_free.empty()) {
+      r.a = g_prof_free.back().first;
+      r.b = g_prof_free.back().second;
+      g_prof_free.pop_back();
+    } else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    r.cls = cls;
+    r.work = work;
+    on = true;
+    cudaEventRecord(r.a, s);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(r);
+  }
+};
+
 int fail(const std::string& msg) {
   g_err = msg;
   return 1;
@@ -279,6 +319,7 @@ int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], in
   p.scale = 1.0f;
   p.reverse_m = 0;
   const int bn = aihab::gemm_block_n(M, N, h->num_sms);
+  ProfScope ps(PC_GEMM, 2.0 * M * N * K, s);
   CKL(aihab::launch_gemm(ma, mw[bn == 256 ? 1 : 0], p, bn, h->num_sms, s));
   return 0;
 }
@@ -290,15 +331,27 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
   if (run_gemm(h, h->m_patches, h->m_conv, n * h->g2, D, h->Kpad, aihab::EPI_PATCH_32, nullptr, nullptr, h->x, D, s))
     return 1;
   // class token row + ln_pre, in place on the fp32 residual stream (clip/model.py:220-222)
-  CKL(aihab::launch_layernorm(h->x, D, h->cls0, L, h->lnpre_g, h->lnpre_b, h->x, nullptr, 0, M, D, s));
+  {
+    ProfScope ps(PC_LN, 8.0 * M * D, s);
+    CKL(aihab::launch_layernorm(h->x, D, h->cls0, L, h->lnpre_g, h->lnpre_b, h->x, nullptr, 0, M, D, s));
+  }
   for (auto& b : h->blocks) {
     // x = x + out_proj(attn(in_proj(ln_1(x))))   (clip/model.py:181,184)
-    CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln1_g, b.ln1_b, nullptr, h->y, h->bf16, M, D, s));
+    {
+      ProfScope ps(PC_LN, 6.0 * M * D, s);
+      CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln1_g, b.ln1_b, nullptr, h->y, h->bf16, M, D, s));
+    }
     if (run_gemm(h, h->m_y, b.m_in, M, 3 * D, D, aihab::EPI_BIAS_16, b.b_in, h->big, nullptr, 3 * D, s)) return 1;
-    CKL(aihab::launch_attention(h->big, h->y, n, L, h->cfg.heads, h->bf16, s));
+    {
+      ProfScope ps(PC_ATTN, 4.0 * n * L * L * D, s);
+      CKL(aihab::launch_attention(h->big, h->y, n, L, h->cfg.heads, h->bf16, s));
+    }
     if (run_gemm(h, h->m_y, b.m_out, M, D, D, aihab::EPI_BIAS_RES_32, b.b_out, nullptr, h->x, D, s)) return 1;
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))   (clip/model.py:171-175,185)
-    CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln2_g, b.ln2_b, nullptr, h->y, h->bf16, M, D, s));
+    {
+      ProfScope ps(PC_LN, 6.0 * M * D, s);
+      CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln2_g, b.ln2_b, nullptr, h->y, h->bf16, M, D, s));
+    }
     if (run_gemm(h, h->m_y, b.m_fc, M, 4 * D, D, aihab::EPI_BIAS_GELU_16, b.b_fc, h->big, nullptr, 4 * D, s))
       return 1;
     if (run_gemm(h, h->m_h, b.m_proj, M, D, 4 * D, aihab::EPI_BIAS_RES_32, b.b_proj, nullptr, h->x, D, s)) return 1;
@@ -321,6 +374,42 @@ extern "C" {
 int aihab_abi_version(void) { return AIHAB_ABI_VERSION; }
 const char* aihab_last_error(void) { return g_err.c_str(); }
 uint64_t aihab_kernel_launches(void) { return g_launches.load(); }
+
+int aihab_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int aihab_profile_read(int cls, double* ms_out, uint64_t* launches_out, double* work_out, int reset) {
+  if (cls < 0 || cls >= PC_COUNT) return fail("aihab_profile_read: bad class");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0.0, work = 0.0;
+  uint64_t cnt = 0;
+  for (const ProfRec& r : g_prof_recs) {
+    if (r.cls != cls) continue;
+    CK(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+    work += r.work;
+    ++cnt;
+  }
+  if (reset) {
+    std::vector<ProfRec> keep;
+    for (const ProfRec& r : g_prof_recs) {
+      if (r.cls == cls)
+        g_prof_free.emplace_back(r.a, r.b);
+      else
+        keep.push_back(r);
+    }
+    g_prof_recs.swap(keep);
+  }
+  if (ms_out) *ms_out = ms;
+  if (launches_out) *launches_out = cnt;
+  if (work_out) *work_out = work;
+  return 0;
+}
 
 int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, int device, aihab_vit** out) {
   if (cfg == nullptr || w == nullptr || out == nullptr) return fail("aihab_vit_create: null argument");
@@ -442,7 +531,10 @@ int aihab_vit_encode(aihab_vit* h, const void* images, int in_dtype, int n, void
   for (int i0 = 0; i0 < n; i0 += h->cfg.max_batch) {
     const int nb = std::min(h->cfg.max_batch, n - i0);
     const uint8_t* src = static_cast<const uint8_t*>(images) + img_bytes * i0;
-    CKL(aihab::launch_im2col(src, in_dtype, nb, R, h->cfg.patch_size, h->Kpad, h->patches, h->bf16, s));
+    {
+      ProfScope ps(PC_PRE, static_cast<double>(nb) * (img_bytes + static_cast<double>(h->g2) * h->Kpad * 2), s);
+      CKL(aihab::launch_im2col(src, in_dtype, nb, R, h->cfg.patch_size, h->Kpad, h->patches, h->bf16, s));
+    }
     void* dst = static_cast<uint8_t*>(feats_out) + static_cast<size_t>(i0) * h->D * dtype_size(out_dtype);
     if (run_tower(h, nb, dst, out_dtype, s)) return 1;
   }
@@ -463,9 +555,12 @@ int aihab_vit_encode_u8(aihab_vit* h, const uint8_t* images_u8, int n, int sh, i
   const size_t img_bytes = static_cast<size_t>(sh) * sw * 3;
   for (int i0 = 0; i0 < n; i0 += h->cfg.max_batch) {
     const int nb = std::min(h->cfg.max_batch, n - i0);
-    CK(aihab::launch_preprocess(images_u8 + img_bytes * i0, nb, sh, sw, R, t, h->patches, h->bf16 ? AIHAB_BF16 : AIHAB_F16,
-                                1, h->cfg.patch_size, h->Kpad, s));
-    g_launches += (h->Kpad > h->Kp) ? 2 : 1;
+    {
+      ProfScope ps(PC_PRE, static_cast<double>(nb) * (img_bytes + static_cast<double>(h->g2) * h->Kpad * 2), s);
+      CK(aihab::launch_preprocess(images_u8 + img_bytes * i0, nb, sh, sw, R, t, h->patches,
+                                  h->bf16 ? AIHAB_BF16 : AIHAB_F16, 1, h->cfg.patch_size, h->Kpad, s));
+      g_launches += (h->Kpad > h->Kp) ? 2 : 1;
+    }
     void* dst = static_cast<uint8_t*>(feats_out) + static_cast<size_t>(i0) * h->D * dtype_size(out_dtype);
     if (run_tower(h, nb, dst, out_dtype, s)) return 1;
   }
@@ -503,6 +598,7 @@ int aihab_score(const float* feats, int n, int D, const float* proj, int E, cons
   const int rows_tmp = std::min(n, chunk);
   if (emb_out == nullptr) CK(cudaMallocAsync(&emb_tmp, static_cast<size_t>(rows_tmp) * E * 4, s));
   if (text_w != nullptr && logits_out == nullptr) CK(cudaMallocAsync(&logit_tmp, static_cast<size_t>(rows_tmp) * C * 4, s));
+  ProfScope ps(PC_SCORE, 2.0 * n * (static_cast<double>(proj ? D : 0) * E + static_cast<double>(text_w ? E : 0) * C), s);
   for (int i0 = 0; i0 < n; i0 += chunk) {
     const int nb = std::min(chunk, n - i0);
     const float* f = feats + static_cast<size_t>(i0) * D;

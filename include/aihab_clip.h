@@ -92,6 +92,13 @@ AIHAB_API const char* aihab_last_error(void);
 /* number of kernels this library has launched in this process (all handles, all streams) */
 AIHAB_API uint64_t aihab_kernel_launches(void);
 
+/* Optional per-kernel-class timing (CUDA events recorded on the launch stream around every launch of the class).
+ * Classes: 0 = tcgen05 GEMM, 1 = attention, 2 = LayerNorm, 3 = im2col / preprocess, 4 = scoring.
+ * aihab_profile_read sums elapsed milliseconds, launches and algorithmic work (FLOPs for 0/1/4, bytes for 2/3)
+ * recorded since the last reset; it synchronises on the recorded events. */
+AIHAB_API int aihab_profile_enable(int on);
+AIHAB_API int aihab_profile_read(int cls, double* ms, uint64_t* launches, double* work, int reset);
+
 /* Image tower -------------------------------------------------------------------------------------------
  * Replaces build_model(...).visual construction + convert_weights (clip/model.py:372-433): packs the weights
  * into 16-bit K-major tensor-core layout, builds TMA descriptors, allocates the workspace on `device`. */

@@ -1,0 +1,177 @@
+"""Per-kernel parity on a B200: every CUDA kernel is called through the C ABI (ctypes) and compared with the
+numpy oracle on the same seeded inputs.  Integer work (preprocessing, top-k indices) must be bit-exact;
+floating-point work is held to tolerances written next to each assert."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from aihab_clip_b200 import _lib, ops
+    return _lib, ops
+
+
+def _rand16(rng, shape, scale, dtype):
+    return torch.from_numpy((scale * rng.standard_normal(shape)).astype(np.float32)).to(dtype)
+
+
+GEMM_SHAPES = [(300, 2304, 768), (389, 768, 3072), (50, 128, 64), (1000, 200, 640), (128, 256, 768),
+               (4100, 3072, 768), (7, 64, 128)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bias_16(cuda_device, dtype, M, N, K):
+    _lib, ops = _ops()
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    a, w = _rand16(rng, (M, K), 1.0, dtype), _rand16(rng, (N, K), K ** -0.5, dtype)
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32))
+    out = torch.full((M, N), float("nan"), dtype=dtype, device=cuda_device)
+    ops.gemm16(a.to(cuda_device), w.to(cuda_device), _lib.EPI_BIAS_16, bias=bias.to(cuda_device), out16=out)
+    torch.cuda.synchronize()
+    ref = a.double().numpy() @ w.double().numpy().T + bias.double().numpy()
+    got = out.float().cpu().numpy()
+    # fp32 accumulation of exact 16-bit products + one rounding to the 16-bit output format
+    eps = 2.0 ** -11 if dtype == torch.float16 else 2.0 ** -8
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, ref, atol=eps * 4 + 1e-4, rtol=eps * 1.01)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 3072, 768), (129, 256, 128)])
+def test_gemm_bias_quickgelu(cuda_device, M, N, K):
+    _lib, ops = _ops()
+    rng = np.random.default_rng(11)
+    a, w = _rand16(rng, (M, K), 1.0, torch.float16), _rand16(rng, (N, K), 2 * K ** -0.5, torch.float16)
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32))
+    out = torch.empty((M, N), dtype=torch.float16, device=cuda_device)
+    ops.gemm16(a.to(cuda_device), w.to(cuda_device), _lib.EPI_BIAS_GELU_16, bias=bias.to(cuda_device), out16=out)
+    u = a.double().numpy() @ w.double().numpy().T + bias.double().numpy()
+    ref = u / (1.0 + np.exp(-1.702 * u))
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref, atol=2e-3, rtol=2.0 ** -10)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 768, 3072), (513, 1024, 1024), (5, 128, 64)])
+def test_gemm_bias_residual_fp32(cuda_device, M, N, K):
+    _lib, ops = _ops()
+    rng = np.random.default_rng(12)
+    a, w = _rand16(rng, (M, K), 1.0, torch.float16), _rand16(rng, (N, K), K ** -0.5, torch.float16)
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32))
+    x0 = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32))
+    x = x0.clone().to(cuda_device)
+    ops.gemm16(a.to(cuda_device), w.to(cuda_device), _lib.EPI_BIAS_RES_32, bias=bias.to(cuda_device), out32=x)
+    ref = x0.double().numpy() + a.double().numpy() @ w.double().numpy().T + bias.double().numpy()
+    np.testing.assert_allclose(x.cpu().numpy(), ref, atol=2e-4, rtol=1e-5)  # fp32 accumulate + fp32 add
+
+
+def test_gemm_patch_embed_epilogue(cuda_device):
+    _lib, ops = _ops()
+    rng = np.random.default_rng(13)
+    n_img, g2, D, K = 5, 49, 256, 640
+    a, w = _rand16(rng, (n_img * g2, K), 1.0, torch.float16), _rand16(rng, (D, K), K ** -0.5, torch.float16)
+    pos = torch.from_numpy(rng.standard_normal((g2 + 1, D)).astype(np.float32))
+    x = torch.zeros(n_img * (g2 + 1), D, dtype=torch.float32, device=cuda_device)
+    ops.gemm16(a.to(cuda_device), w.to(cuda_device), _lib.EPI_PATCH_32, out32=x, pos=pos.to(cuda_device), g2=g2)
+    acc = (a.double().numpy() @ w.double().numpy().T).reshape(n_img, g2, D) + pos.double().numpy()[None, 1:]
+    got = x.cpu().numpy().reshape(n_img, g2 + 1, D)
+    np.testing.assert_allclose(got[:, 1:], acc, atol=2e-4, rtol=1e-5)
+    assert (got[:, 0] == 0).all()  # class-token rows are written by the ln_pre kernel, not the GEMM
+
+
+def test_gemm_scale_fp32(cuda_device):
+    _lib, ops = _ops()
+    rng = np.random.default_rng(14)
+    M, N, K = 777, 1000, 512
+    a, w = _rand16(rng, (M, K), K ** -0.5, torch.float16), _rand16(rng, (N, K), K ** -0.5, torch.float16)
+    out = torch.empty(M, N, dtype=torch.float32, device=cuda_device)
+    ops.gemm16(a.to(cuda_device), w.to(cuda_device), _lib.EPI_SCALE_32, out32=out, scale=100.0)
+    ref = 100.0 * (a.double().numpy() @ w.double().numpy().T)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=1e-4, rtol=1e-5)
+
+
+@pytest.mark.parametrize("D", [128, 768, 1024])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_layernorm(cuda_device, D, out_dtype):
+    _lib, ops = _ops()
+    rng = np.random.default_rng(D)
+    x = (rng.standard_normal((333, D)) * 3 + 0.5).astype(np.float32)
+    g, b = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32), rng.standard_normal(D).astype(np.float32)
+    y = ops.layernorm(torch.from_numpy(x).to(cuda_device), torch.from_numpy(g).to(cuda_device),
+                      torch.from_numpy(b).to(cuda_device), out_dtype)
+    ref = O.layer_norm(x, g, b)
+    tol = {torch.float32: 1e-5, torch.float16: 2.0 ** -10, torch.bfloat16: 2.0 ** -7}[out_dtype]
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref, atol=tol * 4, rtol=tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("L,H,n", [(50, 12, 3), (197, 12, 2), (257, 16, 2), (577, 16, 1), (17, 2, 4), (64, 1, 1)])
+def test_attention(cuda_device, dtype, L, H, n):
+    _lib, ops = _ops()
+    rng = np.random.default_rng(L + H)
+    D = H * 64
+    qkv = _rand16(rng, (n * L, 3 * D), 1.5, dtype)
+    out = ops.attention(qkv.to(cuda_device), n, L, H).float().cpu().numpy()
+    q, k, v = (t.reshape(n, L, H, 64).transpose(0, 2, 1, 3) for t in np.split(qkv.double().numpy(), 3, axis=-1))
+    s = q @ k.transpose(0, 1, 3, 2) / 8.0
+    p = np.exp(s - s.max(-1, keepdims=True))
+    ref = ((p / p.sum(-1, keepdims=True)) @ v).transpose(0, 2, 1, 3).reshape(n * L, D)
+    # P is rounded to 16 bits before PV and the output is 16-bit: error ~ eps * |v|
+    eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    np.testing.assert_allclose(out, ref, atol=eps * 3, rtol=eps * 2)
+
+
+def test_preprocess_bit_exact(cuda_device, gold, meta):
+    _lib, ops = _ops()
+    from aihab_clip_b200.weights import synthetic_images_u8
+    import hashlib
+    for (h, w, R) in meta["pre_cases"]:
+        rng = np.random.Generator(np.random.PCG64([99, h, w, R]))
+        u8 = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+        u8[1] = synthetic_images_u8(1, max(h, w), seed=5, smooth=True)[0][:h, :w]
+        y = ops.preprocess_u8(torch.from_numpy(u8).to(cuda_device), R).cpu().numpy()
+        ref = np.stack([O.clip_preprocess(im, R) for im in u8])
+        np.testing.assert_array_equal(y, ref, err_msg=f"{h}x{w}->{R}")
+        assert hashlib.sha256(y.tobytes()).digest() == gold[f"pre_{h}x{w}_{R}_sha"].tobytes()
+    # 16-bit outputs are the fp32 result rounded once
+    u8 = synthetic_images_u8(3, 439)
+    y32 = ops.preprocess_u8(torch.from_numpy(u8).to(cuda_device), 224)
+    y16 = ops.preprocess_u8(torch.from_numpy(u8).to(cuda_device), 224, torch.float16)
+    assert torch.equal(y16, y32.half())
+
+
+@pytest.mark.parametrize("n,D,E,Cn,k", [(64, 768, 512, 20, 3), (1000, 768, 512, 1000, 5), (5, 128, 64, 18, 1)])
+def test_score_matches_oracle(cuda_device, n, D, E, Cn, k):
+    _lib, ops = _ops()
+    rng = np.random.default_rng(n + Cn)
+    feats = rng.standard_normal((n, D)).astype(np.float32)
+    proj = (D ** -0.5 * rng.standard_normal((D, E))).astype(np.float32)
+    tw = O.l2_normalize(rng.standard_normal((Cn, E)).astype(np.float32)).T.copy()
+    emb, logits, idx, val = ops.score(torch.from_numpy(feats).to(cuda_device), torch.from_numpy(proj).to(cuda_device),
+                                      torch.from_numpy(tw).to(cuda_device), 100.0, k)
+    r_emb, r_logits, r_idx = O.score(feats, proj, tw, 100.0, k)
+    np.testing.assert_allclose(emb.cpu().numpy(), r_emb, atol=2e-6, rtol=0)
+    np.testing.assert_allclose(logits.cpu().numpy(), r_logits, atol=2e-4, rtol=0)
+    # top-k of the kernel's own logits is exact (torch.topk semantics, lowest index first among ties)
+    np.testing.assert_array_equal(idx.cpu().numpy(), O.topk_indices(logits.cpu().numpy(), k))
+    srt = np.sort(r_logits, axis=1)[:, ::-1][:, :k + 1]
+    untied = np.abs(np.diff(srt, axis=1)).min(axis=1) > 1e-3
+    np.testing.assert_array_equal(idx.cpu().numpy()[untied], r_idx[untied])
+    np.testing.assert_array_equal(val.cpu().numpy(), np.take_along_axis(logits.cpu().numpy(), idx.cpu().numpy(), 1))
+
+
+def test_topk_exact_ties(cuda_device):
+    _lib, ops = _ops()
+    lg = np.zeros((4, 8), dtype=np.float32)
+    lg[0] = [1, 3, 3, 2, 3, 0, -1, 2]
+    lg[1] = 5
+    lg[2] = np.arange(8)
+    lg[3] = -np.arange(8)
+    # score() with identity projection-free path: feats are one-hot rows so logits = scale * text_w rows
+    eye = torch.eye(4, dtype=torch.float32, device=cuda_device)
+    emb, logits, idx, _ = ops.score(eye, None, torch.from_numpy(lg).to(cuda_device), 1.0, 4)
+    np.testing.assert_array_equal(logits.cpu().numpy(), lg)
+    np.testing.assert_array_equal(idx.cpu().numpy(), O.topk_indices(lg, 4))
+    assert idx[0].tolist() == [1, 2, 4, 3] and idx[1].tolist() == [0, 1, 2, 3]

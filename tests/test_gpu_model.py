@@ -1,0 +1,126 @@
+"""End-to-end parity of the image tower + scoring on a B200 against (a) the golden outputs of the unmodified
+reference (tests/golden) and (b) the numpy oracle on the same seeded inputs.  Gates from BASELINE.json:
+embedding cosine >= 0.999, max |dlogit| <= 1e-2 on the x100 logits, argmax agreement, top-k exact where the
+reference scores are untied."""
+import numpy as np
+import pytest
+import torch
+
+from aihab_clip_b200.weights import GEOMETRIES, make_state_dict, make_state_dict_np, synthetic_images_u8
+from oracle import clip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = {"tiny16": ("ViT-tiny/16", 0, 6, 64), "tiny14": ("ViT-tiny/14", 1, 6, 111), "b32": ("ViT-B/32", 0, 8, 439)}
+
+
+def load_model(tmp_path, geom, seed, device, compute_dtype="fp16"):
+    import aihab_clip_b200.clip as clip
+    path = tmp_path / "ckpt.pt"
+    torch.save(make_state_dict(geom, seed), path)
+    state, model, preprocess = clip.load(str(path), device=device)
+    model.visual.compute_dtype = compute_dtype
+    return state, model, preprocess
+
+
+def case_images(tag):
+    geom, seed, n, side = CASES[tag]
+    u8 = np.concatenate([synthetic_images_u8(n // 2, side, seed=1234),
+                         synthetic_images_u8(n - n // 2, side, seed=1234, start=n // 2, smooth=True)])
+    return GEOMETRIES[geom], seed, u8
+
+
+def cosine(a, b):
+    return (a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))
+
+
+@pytest.mark.parametrize("tag", ["tiny16", "tiny14", "b32"])
+def test_encode_image_matches_reference_golden(tmp_path, cuda_device, gold, tag):
+    geom, seed, u8 = case_images(tag)
+    state, model, preprocess = load_model(tmp_path, geom.name, seed, cuda_device)
+    assert model.dtype == torch.float16  # clip.load on CUDA keeps the reference's fp16 parameters
+    model.float()                         # fp32 in/out like the CPU reference run that made the goldens
+    R = geom.image_resolution
+    x = preprocess.batch_u8(torch.from_numpy(u8).to(cuda_device))
+    ref_x = np.stack([O.clip_preprocess(im, R) for im in u8])
+    np.testing.assert_array_equal(x.cpu().numpy(), ref_x)
+    feats = model.encode_image(x)
+    assert feats.dtype == torch.float32 and tuple(feats.shape) == (len(u8), geom.vision_width)
+    f = feats.cpu().numpy()
+    ref_f = gold[f"{tag}_feats"]
+    assert cosine(f, ref_f).min() >= 0.999
+    # pre-projection features are O(1) after ln_post; fp16 operands, fp32 accumulation/residual/LN
+    np.testing.assert_allclose(f, ref_f, atol=1e-2, rtol=0)
+
+    from aihab_clip_b200 import ops
+    text_w = torch.from_numpy(gold[f"{tag}_text_w"]).to(cuda_device)
+    emb, logits, idx, _ = ops.score(feats, model.visual.proj, text_w, 100.0, 3)
+    assert cosine(emb.cpu().numpy(), gold[f"{tag}_emb"]).min() >= 0.999
+    ref_logits = gold[f"{tag}_logits"]
+    err = np.abs(logits.cpu().numpy() - ref_logits).max()
+    assert err <= 1e-2, f"max |dlogit| = {err}"
+    srt = np.sort(ref_logits, axis=1)[:, ::-1]
+    untied1 = (srt[:, 0] - srt[:, 1]) > 2 * err
+    assert (idx[:, 0].cpu().numpy()[untied1] == gold[f"{tag}_argmax"][untied1]).all()
+    untied3 = np.abs(np.diff(srt[:, :4], axis=1)).min(axis=1) > 2 * err
+    np.testing.assert_array_equal(idx.cpu().numpy()[untied3], gold[f"{tag}_top3"][untied3])
+
+    # fused uint8 path == preprocess + encode, bit for bit
+    f_u8 = model.encode_image_u8(torch.from_numpy(u8).to(cuda_device))
+    assert torch.equal(f_u8, feats)
+
+
+@pytest.mark.parametrize("compute_dtype,logit_tol", [("fp16", 1e-2), ("bf16", 6e-2)])
+def test_operand_formats_vs_oracle(tmp_path, cuda_device, gold, compute_dtype, logit_tol):
+    """fp16 operands meet the 1e-2 logit gate; single-pass bf16 operands are ~3x over it and are
+    held to 6e-2 here so the gap stays visible."""
+    geom, seed, u8 = case_images("b32")
+    _, model, preprocess = load_model(tmp_path, geom.name, seed, cuda_device, compute_dtype)
+    model.float()
+    x = preprocess.batch_u8(torch.from_numpy(u8).to(cuda_device))
+    feats = model.encode_image(x)
+    from aihab_clip_b200 import ops
+    _, logits, _, _ = ops.score(feats, model.visual.proj, torch.from_numpy(gold["b32_text_w"]).to(cuda_device), 100.0, 1)
+    assert cosine(feats.cpu().numpy(), gold["b32_feats"]).min() >= 0.999
+    assert np.abs(logits.cpu().numpy() - gold["b32_logits"]).max() <= logit_tol
+
+
+def test_batch_composition_invariance_and_chunking(tmp_path, cuda_device):
+    """Per-image results must not depend on batch composition (needed for sharding), including
+    across the internal max_batch chunk boundary."""
+    geom = GEOMETRIES["ViT-tiny/16"]
+    _, model, preprocess = load_model(tmp_path, geom.name, 0, cuda_device)
+    model.float()
+    model.visual.max_batch = 4
+    u8 = torch.from_numpy(synthetic_images_u8(11, 64)).to(cuda_device)
+    x = preprocess.batch_u8(u8)
+    all_f = model.encode_image(x)            # 3 chunks: 4 + 4 + 3
+    for i in (0, 3, 4, 10):
+        assert torch.equal(model.encode_image(x[i:i + 1]), all_f[i:i + 1])
+    assert torch.equal(model.encode_image(x[5:9]), all_f[5:9])
+    assert model.encode_image(x[:0]).shape == (0, geom.vision_width)
+
+
+def test_fp16_model_dtype_roundtrip(tmp_path, cuda_device, gold):
+    """Reference GPU behaviour: fp16 parameters, fp16 images in, fp16 features out (clip/model.py:331-336)."""
+    geom, seed, u8 = case_images("tiny16")
+    state, model, preprocess = load_model(tmp_path, geom.name, seed, cuda_device)
+    x = preprocess.batch_u8(torch.from_numpy(u8).to(cuda_device))
+    feats = model.encode_image(x)            # fp32 input is cast to model.dtype first
+    assert feats.dtype == torch.float16
+    assert cosine(feats.float().cpu().numpy(), gold["tiny16_feats"]).min() >= 0.999
+    assert state["visual.proj"].dtype == torch.float16
+    xb, xt = model.encode_text(torch.from_numpy(gold["tiny16_tok"]).to(cuda_device))
+    np.testing.assert_allclose(xt.detach().float().cpu().numpy(), gold["tiny16_text_emb"], atol=2e-2, rtol=0)
+
+
+def test_errors_are_python_exceptions(tmp_path, cuda_device):
+    geom = GEOMETRIES["ViT-tiny/16"]
+    _, model, _ = load_model(tmp_path, geom.name, 0, cuda_device)
+    with pytest.raises(RuntimeError):
+        model.encode_image(torch.zeros(1, 3, 32, 32, device=cuda_device))
+    with pytest.raises(RuntimeError):
+        model.encode_image(torch.zeros(1, 3, 64, 64))  # CPU tensor: no fallback
+    import aihab_clip_b200.clip as clip
+    with pytest.raises(RuntimeError):
+        clip.load("/nonexistent/model.pt")
