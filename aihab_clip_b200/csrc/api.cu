@@ -253,7 +253,7 @@ struct aihab_vit {
   float* x = nullptr;       // [cap_rows, D] fp32 residual stream
   void* y = nullptr;        // [cap_rows, D] 16-bit (LN output / attention output)
   void* big = nullptr;      // [cap_rows, 4D] 16-bit (qkv [.,3D] and MLP hidden [.,4D] share it)
-  CUtensorMap m_patches, m_y, m_h;
+  CUtensorMap m_patches, m_y, m_h, m_x;  // m_x: fp32 residual stream, {32,32} boxes (EPI_BIAS_RES_32)
   size_t ws_bytes = 0;
   std::vector<void*> allocs;
 };
@@ -320,7 +320,8 @@ int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], in
   p.reverse_m = 0;
   const int bn = aihab::gemm_block_n(M, N, h->num_sms);
   ProfScope ps(PC_GEMM, 2.0 * M * N * K, s);
-  CKL(aihab::launch_gemm(ma, mw[bn == 256 ? 1 : 0], p, bn, h->num_sms, s));
+  CKL(aihab::launch_gemm(ma, mw[bn == 256 ? 1 : 0], epi == aihab::EPI_BIAS_RES_32 ? &h->m_x : nullptr, p, bn,
+                         h->num_sms, s));
   return 0;
 }
 
@@ -500,7 +501,8 @@ int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, in
   }
   if (aihab::make_tmap_2d_16bit(&h->m_patches, h->patches, prow, h->Kpad, static_cast<uint64_t>(h->Kpad) * 2, 128, h->bf16) != cudaSuccess ||
       aihab::make_tmap_2d_16bit(&h->m_y, h->y, h->cap_rows, D, static_cast<uint64_t>(D) * 2, 128, h->bf16) != cudaSuccess ||
-      aihab::make_tmap_2d_16bit(&h->m_h, h->big, h->cap_rows, 4 * D, static_cast<uint64_t>(4 * D) * 2, 128, h->bf16) != cudaSuccess) {
+      aihab::make_tmap_2d_16bit(&h->m_h, h->big, h->cap_rows, 4 * D, static_cast<uint64_t>(4 * D) * 2, 128, h->bf16) != cudaSuccess ||
+      aihab::make_tmap_2d_f32_box32(&h->m_x, h->x, h->cap_rows, D, static_cast<uint64_t>(D) * 4) != cudaSuccess) {
     fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the workspace");
     return bail(1);
   }
@@ -648,7 +650,13 @@ int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype
   p.pos = pos;
   p.g2 = g2;
   p.scale = scale;
-  CKL(aihab::launch_gemm(ma, mw, p, bn, sms, static_cast<cudaStream_t>(stream)));
+  CUtensorMap mc;
+  const bool res = epilogue == AIHAB_EPI_BIAS_RES_32;
+  if (res) {
+    if (out32 == nullptr || (N & 31)) return fail("aihab_gemm16: EPI_BIAS_RES_32 needs out32 and N % 32 == 0");
+    CK(aihab::make_tmap_2d_f32_box32(&mc, out32, M, N, static_cast<uint64_t>(ldo) * 4));
+  }
+  CKL(aihab::launch_gemm(ma, mw, res ? &mc : nullptr, p, bn, sms, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

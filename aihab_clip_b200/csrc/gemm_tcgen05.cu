@@ -14,23 +14,30 @@ constexpr int UMMA_K = 16;   // fixed for 16-bit operands
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;  // warps 4..7 are the epilogue (warp % 4 selects the TMEM lane quadrant)
 
-template <int BN>
+constexpr int RS = 4;           // residual ring slots per epilogue warp (EPI_BIAS_RES_32)
+constexpr int RES_BOX = 32 * 128;  // 32 rows x 32 fp32 = 4 KB TMA box, SWIZZLE_128B
+
+template <int BN, int EPI>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr bool kRes = (EPI == EPI_BIAS_RES_32);
+  // the residual epilogue trades one (BN=256) / two (BN=128) operand stages for a 64 KB TMA ring: those GEMMs are
+  // bound by the fp32 residual read-modify-write, not by the MMA pipe
+  static constexpr int kStages = (BN == 256) ? (kRes ? 3 : 4) : (kRes ? 4 : 6);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = 4 * 32 * 128;  // per epilogue warp: 32 rows x 128 B
+  static constexpr int kStagingBytes = kRes ? 4 * RS * RES_BOX : 4 * 32 * 128;  // per epilogue warp
   static constexpr int kBiasBytes = 2 * BN * 4;
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kStages * kABytes;
   static constexpr int kOffStaging = kStages * kStageBytes;
   static constexpr int kOffBias = kOffStaging + kStagingBytes;
   static constexpr int kOffBars = kOffBias + kBiasBytes;
-  static constexpr int kNumBars = 2 * kStages + 4;
+  static constexpr int kNumBars = 2 * kStages + 4 + 4 * RS;
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemSlot + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
+  static_assert(kDynamic <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
@@ -41,8 +48,8 @@ __device__ __forceinline__ float quick_gelu(float x) {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-            const GemmParams p) {
-  using L = SmemLayout<BN>;
+            const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+  using L = SmemLayout<BN, EPI>;
   constexpr int kStages = L::kStages;
   constexpr bool kOut16 = (EPI == EPI_BIAS_16 || EPI == EPI_BIAS_GELU_16);
 
@@ -56,6 +63,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* res_full_bar = tmem_empty_bar + 2;  // [4 epilogue warps][RS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
 
   const int warp = threadIdx.x >> 5;
@@ -79,6 +87,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       ptx::mbar_init(&tmem_full_bar[i], 1);
       ptx::mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
     }
+    for (int i = 0; i < 4 * RS; ++i) ptx::mbar_init(&res_full_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -150,6 +159,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint8_t* stg = sStaging + ew * (32 * 128);
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
     const bool bf16 = p.ab_format != 0;
+    // EPI_BIAS_RES_32: every warp streams its 32-row slice of the fp32 residual through a private ring of 4 KB
+    // TMA boxes (load -> add in place -> TMA store), prefetching RS-1 boxes ahead across tile boundaries.
+    constexpr int CPT = BN / 32;  // residual boxes per tile per warp
+    uint64_t* my_full = res_full_bar + ew * RS;
+    uint8_t* my_ring = sStaging + ew * (RS * RES_BOX);
+    auto res_prefetch = [&](int q) {  // lane 0 only: issue the TMA load of this warp's q-th box, if it exists
+      const int itq = q / CPT, cq = q - itq * CPT;
+      const long tq = static_cast<long>(blockIdx.x) + static_cast<long>(itq) * gridDim.x;
+      if (tq >= num_tiles) return;
+      int mb = static_cast<int>(tq / n_blocks);
+      const int nb = static_cast<int>(tq - static_cast<long>(mb) * n_blocks);
+      if (p.reverse_m) mb = m_blocks - 1 - mb;
+      const int slot = q % RS;
+      ptx::mbar_expect_tx(&my_full[slot], RES_BOX);
+      ptx::tma_load_2d(my_ring + slot * RES_BOX, &tmap_c, &my_full[slot], nb * BN + cq * 32, mb * BM + ew * 32);
+    };
+    int q = 0;  // running box counter of this warp
+    if constexpr (EPI == EPI_BIAS_RES_32) {
+      if (lane == 0) {
+        for (int i = 0; i < RS - 1; ++i) res_prefetch(i);
+      }
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int m_blk = tile / n_blocks;
@@ -213,6 +244,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + static_cast<size_t>(grow) * p.ldo +
                                         gcol) = v;
             }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (EPI == EPI_BIAS_RES_32) {
+#pragma unroll 1
+        for (int c = 0; c < CPT; ++c, ++q) {
+          const int slot = q % RS;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, r);
+          ptx::mbar_wait(&my_full[slot], (q / RS) & 1);
+          ptx::tmem_ld_wait();
+          uint8_t* box = my_ring + slot * RES_BOX;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4* px = reinterpret_cast<float4*>(box + lane * 128 + ((u ^ (lane & 7)) << 4));
+            float4 v = *px;
+            v.x += __uint_as_float(r[4 * u]) + sb[c * 32 + 4 * u];
+            v.y += __uint_as_float(r[4 * u + 1]) + sb[c * 32 + 4 * u + 1];
+            v.z += __uint_as_float(r[4 * u + 2]) + sb[c * 32 + 4 * u + 2];
+            v.w += __uint_as_float(r[4 * u + 3]) + sb[c * 32 + 4 * u + 3];
+            *px = v;
+          }
+          ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_c, box, n0 + c * 32, m0);
+            ptx::bulk_commit();
+            ptx::bulk_wait_read<1>();   // the store issued one box ago has finished reading its slot ...
+            res_prefetch(q + RS - 1);   // ... which is exactly the slot box q+RS-1 lands in
           }
           __syncwarp();
         }
@@ -282,6 +342,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
     }
+    if constexpr (EPI == EPI_BIAS_RES_32) {
+      if (lane == 0) ptx::bulk_wait_all();  // smem must outlive the last TMA stores
+    }
   }
 
   ptx::tc_fence_before();
@@ -297,25 +360,25 @@ PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 template <int BN, int EPI>
 cudaError_t set_attr() {
   return cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              SmemLayout<BN>::kDynamic);
+                              SmemLayout<BN, EPI>::kDynamic);
 }
 
 template <int BN, int EPI>
-cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, int grid,
-                       cudaStream_t stream) {
-  gemm_kernel<BN, EPI><<<grid, NUM_THREADS, SmemLayout<BN>::kDynamic, stream>>>(ta, tw, p);
+cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const GemmParams& p,
+                       int grid, cudaStream_t stream) {
+  gemm_kernel<BN, EPI><<<grid, NUM_THREADS, SmemLayout<BN, EPI>::kDynamic, stream>>>(ta, tw, tc, p);
   return cudaGetLastError();
 }
 
 template <int BN>
-cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, int grid,
-                      cudaStream_t stream) {
+cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const GemmParams& p,
+                      int grid, cudaStream_t stream) {
   switch (p.epilogue) {
-    case EPI_BIAS_16: return launch_one<BN, EPI_BIAS_16>(ta, tw, p, grid, stream);
-    case EPI_BIAS_GELU_16: return launch_one<BN, EPI_BIAS_GELU_16>(ta, tw, p, grid, stream);
-    case EPI_BIAS_RES_32: return launch_one<BN, EPI_BIAS_RES_32>(ta, tw, p, grid, stream);
-    case EPI_PATCH_32: return launch_one<BN, EPI_PATCH_32>(ta, tw, p, grid, stream);
-    case EPI_SCALE_32: return launch_one<BN, EPI_SCALE_32>(ta, tw, p, grid, stream);
+    case EPI_BIAS_16: return launch_one<BN, EPI_BIAS_16>(ta, tw, tc, p, grid, stream);
+    case EPI_BIAS_GELU_16: return launch_one<BN, EPI_BIAS_GELU_16>(ta, tw, tc, p, grid, stream);
+    case EPI_BIAS_RES_32: return launch_one<BN, EPI_BIAS_RES_32>(ta, tw, tc, p, grid, stream);
+    case EPI_PATCH_32: return launch_one<BN, EPI_PATCH_32>(ta, tw, tc, p, grid, stream);
+    case EPI_SCALE_32: return launch_one<BN, EPI_SCALE_32>(ta, tw, tc, p, grid, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -371,19 +434,38 @@ int gemm_block_n(int M, int N, int num_sms) {
   return cost128 < cost256 ? 128 : 256;
 }
 
-cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, const GemmParams& p, int block_n,
-                        int num_sms, cudaStream_t stream) {
+cudaError_t make_tmap_2d_f32_box32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                                   uint64_t row_pitch_bytes) {
+  if (g_encode == nullptr) {
+    cudaError_t e = gemm_init();
+    if (e != cudaSuccess) return e;
+  }
+  if ((row_pitch_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return cudaErrorInvalidValue;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, const CUtensorMap* tmap_c,
+                        const GemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorInvalidValue;
   const bool out16 = (p.epilogue == EPI_BIAS_16 || p.epilogue == EPI_BIAS_GELU_16);
   if (out16 && ((p.N & 7) || (p.ldo & 7) || p.out16 == nullptr)) return cudaErrorInvalidValue;
   if (!out16 && ((p.N & 3) || (p.ldo & 3) || p.out32 == nullptr)) return cudaErrorInvalidValue;
   if (p.epilogue == EPI_PATCH_32 && (p.pos == nullptr || p.g2 <= 0)) return cudaErrorInvalidValue;
+  if (p.epilogue == EPI_BIAS_RES_32 && (tmap_c == nullptr || (p.N & 31))) return cudaErrorInvalidValue;
+  const CUtensorMap& tc = tmap_c ? *tmap_c : tmap_a;  // unused by the other epilogues
   const int m_blocks = (p.M + BM - 1) / BM;
   const int n_blocks = (p.N + block_n - 1) / block_n;
   const long tiles = static_cast<long>(m_blocks) * n_blocks;
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
-  if (block_n == 256) return launch_bn<256>(tmap_a, tmap_w, p, grid, stream);
-  if (block_n == 128) return launch_bn<128>(tmap_a, tmap_w, p, grid, stream);
+  if (block_n == 256) return launch_bn<256>(tmap_a, tmap_w, tc, p, grid, stream);
+  if (block_n == 128) return launch_bn<128>(tmap_a, tmap_w, tc, p, grid, stream);
   return cudaErrorInvalidValue;
 }
 

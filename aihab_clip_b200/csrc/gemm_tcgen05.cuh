@@ -45,9 +45,15 @@ struct GemmParams {
 cudaError_t make_tmap_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                                uint64_t row_pitch_bytes, uint32_t box_rows, int ab_format);
 
-// Launches the GEMM.  tmap_a box = {64,128}; tmap_w box = {64,BN} with BN = gemm_block_n(N, M).
-cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, const GemmParams& p, int block_n,
-                        int num_sms, cudaStream_t stream);
+// Tensor map over the fp32 residual stream [rows, cols] with a {32 cols, 32 rows} box (4 KB) and SWIZZLE_128B:
+// used by EPI_BIAS_RES_32 to load, and store back in place, the residual slice of every epilogue warp.
+cudaError_t make_tmap_2d_f32_box32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                                   uint64_t row_pitch_bytes);
+
+// Launches the GEMM.  tmap_a box = {64,128}; tmap_w box = {64,BN} with BN = gemm_block_n(N, M);
+// tmap_c (EPI_BIAS_RES_32 only, N % 32 == 0) = make_tmap_2d_f32_box32 over out32.
+cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, const CUtensorMap* tmap_c,
+                        const GemmParams& p, int block_n, int num_sms, cudaStream_t stream);
 
 // Tile-N policy shared by map construction and launch.
 int gemm_block_n(int M, int N, int num_sms);
