@@ -594,6 +594,11 @@ int aihab_score(const float* feats, int n, int D, const float* proj, int E, cons
   const int dev = device_of(feats);
   DeviceGuard guard(dev);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (aihab::score_fused_supported(n, D, E, text_w ? C : 0)) {
+    ProfScope ps(PC_SCORE, 2.0 * n * (static_cast<double>(proj ? D : 0) * E + static_cast<double>(text_w ? E : 0) * C), s);
+    CKL(aihab::launch_score_fused(feats, n, D, proj, E, text_w, C, scale, k, emb_out, logits_out, topk_idx, topk_val, s));
+    return 0;
+  }
   // rows per pass bounded so temporaries stay small (config 5: 1M rows x 1000 classes)
   const int chunk = 65536;
   float *emb_tmp = nullptr, *logit_tmp = nullptr;

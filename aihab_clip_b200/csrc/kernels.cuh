@@ -43,6 +43,12 @@ cudaError_t launch_l2norm(const float* x, float* y, int rows, int cols, float ep
 cudaError_t launch_topk(const float* logits, int rows, int cols, int k, int64_t* idx, float* val,
                         cudaStream_t stream);
 
+// One-launch small-batch scoring (n <= 8192): proj -> normalise -> logits -> top-k; bit-identical to the chain above.
+bool score_fused_supported(int n, int D, int E, int C);
+cudaError_t launch_score_fused(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C,
+                               float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx,
+                               float* topk_val, cudaStream_t stream);
+
 // ---- preprocessing (data/clip_transforms.py:50-56; Pillow ImagingResample fixed-point bicubic)
 struct ResampleTables {
   // device pointers; *_bounds = {first input index, tap count} per output index; coeffs [out, ksize] int32 (2^22)

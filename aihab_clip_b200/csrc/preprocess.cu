@@ -102,6 +102,61 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   }
 }
 
+// Fast path when the input already has the crop size (new == in, Pillow skips both passes): one thread converts 16
+// consecutive pixels of one image row (48 contiguous input bytes, 3 x 128-bit loads) into three 32-byte runs of the
+// im2col row (one per channel).  Requires p % 16 == 0 (ViT-B/16, ViT-B/32) so a run never straddles a patch.
+template <bool BF16>
+__global__ void __launch_bounds__(256) normalize_im2col16_kernel(const uint8_t* __restrict__ in, int n, int sh, int sw,
+                                                                 int R, int top, int left, uint16_t* __restrict__ out,
+                                                                 int p, int Kpad) {
+  const int segs = R >> 4;
+  const long total = static_cast<long>(n) * R * segs;
+  const int g = R / p;
+  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int xs = static_cast<int>(idx % segs);
+    const long t = idx / segs;
+    const int y = static_cast<int>(t % R);
+    const int img = static_cast<int>(t / R);
+    const uint8_t* src = in + ((static_cast<size_t>(img) * sh + top + y) * sw + left + xs * 16) * 3;
+    uint32_t w[12];  // 48 bytes = 16 RGB pixels
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        w[4 * i] = v.x;
+        w[4 * i + 1] = v.y;
+        w[4 * i + 2] = v.z;
+        w[4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i)
+        w[i] = __ldg(src + 4 * i) | (__ldg(src + 4 * i + 1) << 8) | (__ldg(src + 4 * i + 2) << 16) |
+               (static_cast<uint32_t>(__ldg(src + 4 * i + 3)) << 24);
+    }
+    auto px = [&](int i) { return static_cast<float>((w[i >> 2] >> ((i & 3) * 8)) & 0xffu); };
+    const int x0 = xs * 16;
+    const int gy = y / p, ky = y - gy * p, gx = x0 / p, kx = x0 - gx * p;
+    uint16_t* dst = out + (static_cast<size_t>(img) * g * g + gy * g + gx) * Kpad + ky * p + kx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = (px((2 * j) * 3 + c) / 255.0f - mean[c]) / stdv[c];
+        const float b = (px((2 * j + 1) * 3 + c) / 255.0f - mean[c]) / stdv[c];
+        pk[j] = ptx::pack2<BF16>(a, b);
+      }
+      uint4* d = reinterpret_cast<uint4*>(dst + c * p * p);
+      d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+  }
+}
+
 // zero the K padding columns of im2col rows (layout 1 writes only the first 3*p*p columns)
 __global__ void zero_pad_kernel(uint16_t* out, long rows, int K, int Kpad) {
   const int w = Kpad - K;
@@ -142,6 +197,18 @@ cudaError_t launch_preprocess(const uint8_t* in, int n, int sh, int sw, int R, c
     const int scale_up = (sh + t.new_h - 1) / t.new_h;  // ceil(in / out)
     max_rows = TH * scale_up + t.v_ksize + 2;
     if (max_rows > sh) max_rows = sh;
+  }
+  if (layout == 1 && !t.need_h && !t.need_v && (p % 16) == 0 && (R % 16) == 0 && Kpad == 3 * p * p &&
+      out_dtype != 0) {
+    const long total = static_cast<long>(n) * R * (R / 16);
+    const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 16));
+    if (out_dtype == 2)
+      normalize_im2col16_kernel<true><<<grid, 256, 0, stream>>>(in, n, sh, sw, R, t.crop_top, t.crop_left,
+                                                                static_cast<uint16_t*>(out), p, Kpad);
+    else
+      normalize_im2col16_kernel<false><<<grid, 256, 0, stream>>>(in, n, sh, sw, R, t.crop_top, t.crop_left,
+                                                                 static_cast<uint16_t*>(out), p, Kpad);
+    return cudaGetLastError();
   }
   if (layout == 1 && Kpad > 3 * p * p) {
     const long rows = static_cast<long>(n) * (R / p) * (R / p);

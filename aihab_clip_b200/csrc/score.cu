@@ -115,7 +115,181 @@ __global__ void __launch_bounds__(128) topk_kernel(const float* __restrict__ log
   }
 }
 
+// Small-batch path (one extraction batch): proj -> L2 normalise -> scaled logits -> top-k in ONE launch.
+// RPB rows per CTA share every visual.proj / text-weight element they load.  Thread layout for the projection:
+// 128 column quads (float4 loads of one contiguous proj row per k) x 2 halves of K, 8 loads in flight per thread;
+// per-row reduction order is fixed, so results do not depend on batch composition.
+constexpr int RPB = 4;
+
+__global__ void __launch_bounds__(256) score_fused_kernel(const float* __restrict__ feats, int n, int D,
+                                                          const float* __restrict__ proj, int E,
+                                                          const float* __restrict__ text_w, int C, float scale, int k,
+                                                          float* __restrict__ emb_out, float* __restrict__ logits_out,
+                                                          int64_t* __restrict__ topk_idx, float* __restrict__ topk_val) {
+  extern __shared__ __align__(16) float sm[];
+  float* sf = sm;                 // [RPB][D]
+  float* se = sf + RPB * D;       // [2][RPB][E] partial sums, then [RPB][E] embeddings in the first half
+  float* sl = se + 2 * RPB * E;   // [RPB][C]
+  __shared__ float s_den[RPB];
+  const int row0 = blockIdx.x * RPB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < RPB * D; i += 256) {
+    const int r = i / D;
+    sf[i] = (row0 + r < n) ? feats[static_cast<size_t>(row0 + r) * D + (i - r * D)] : 0.f;
+  }
+  __syncthreads();
+  if (proj != nullptr) {
+    const int half = tid >> 7, q = tid & 127;
+    const int k0 = half * (D / 2), k1 = half ? D : D / 2;
+    for (int e0 = q * 4; e0 < E; e0 += 512) {
+      float4 acc[RPB];
+#pragma unroll
+      for (int r = 0; r < RPB; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int kk = k0;
+      for (; kk + 8 <= k1; kk += 8) {
+        float4 w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(proj + static_cast<size_t>(kk + j) * E + e0));
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int r = 0; r < RPB; ++r) {
+            const float f = sf[r * D + kk + j];
+            acc[r].x = fmaf(f, w[j].x, acc[r].x);
+            acc[r].y = fmaf(f, w[j].y, acc[r].y);
+            acc[r].z = fmaf(f, w[j].z, acc[r].z);
+            acc[r].w = fmaf(f, w[j].w, acc[r].w);
+          }
+      }
+      for (; kk < k1; ++kk) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(proj + static_cast<size_t>(kk) * E + e0));
+#pragma unroll
+        for (int r = 0; r < RPB; ++r) {
+          const float f = sf[r * D + kk];
+          acc[r].x = fmaf(f, w.x, acc[r].x);
+          acc[r].y = fmaf(f, w.y, acc[r].y);
+          acc[r].z = fmaf(f, w.z, acc[r].z);
+          acc[r].w = fmaf(f, w.w, acc[r].w);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RPB; ++r) *reinterpret_cast<float4*>(se + (half * RPB + r) * E + e0) = acc[r];
+    }
+    __syncthreads();
+    for (int i = tid; i < RPB * E; i += 256) se[i] += se[RPB * E + i];
+  } else {
+    for (int i = tid; i < RPB * E; i += 256) se[i] = sf[(i / E) * D + (i % E)];
+  }
+  __syncthreads();
+  if (warp < RPB) {  // F.normalize: x / max(||x||, 1e-12)
+    float s = 0.f;
+    for (int c = lane; c < E; c += 32) s = fmaf(se[warp * E + c], se[warp * E + c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_den[warp] = fmaxf(sqrtf(s), 1e-12f);
+  }
+  __syncthreads();
+  for (int i = tid; i < RPB * E; i += 256) {
+    const int r = i / E;
+    const float v = se[i] / s_den[r];
+    se[i] = v;
+    if (emb_out != nullptr && row0 + r < n) emb_out[static_cast<size_t>(row0 + r) * E + (i - r * E)] = v;
+  }
+  __syncthreads();
+  if (text_w == nullptr) return;
+  if (C <= 64) {
+    // few classes: one warp per class, lanes split E, shuffle-tree reduction
+    for (int c = warp; c < C; c += 8) {
+      float acc[RPB] = {};
+      for (int e = lane; e < E; e += 32) {
+        const float w = __ldg(text_w + static_cast<size_t>(e) * C + c);
+#pragma unroll
+        for (int r = 0; r < RPB; ++r) acc[r] = fmaf(scale * se[r * E + e], w, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < RPB; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < RPB; ++r) sl[r * C + c] = acc[r];
+      }
+    }
+  } else {
+    // many classes: one thread per class, coalesced reads of the [E, C] text matrix
+    for (int c = tid; c < C; c += 256) {
+      float acc[RPB] = {};
+      for (int e = 0; e < E; ++e) {
+        const float w = __ldg(text_w + static_cast<size_t>(e) * C + c);
+#pragma unroll
+        for (int r = 0; r < RPB; ++r) acc[r] = fmaf(scale * se[r * E + e], w, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < RPB; ++r) sl[r * C + c] = acc[r];
+    }
+  }
+  __syncthreads();
+  if (logits_out != nullptr) {
+    for (int i = tid; i < RPB * C; i += 256) {
+      const int r = i / C;
+      if (row0 + r < n) logits_out[static_cast<size_t>(row0 + r) * C + (i - r * C)] = sl[i];
+    }
+  }
+  if (k > 0 && warp < RPB && row0 + warp < n) {
+    const float* src = sl + warp * C;
+    float last_v = INFINITY;
+    int last_i = -1;
+    for (int j = 0; j < k; ++j) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int c = lane; c < C; c += 32) {
+        const float v = src[c];
+        if (precedes(last_v, last_i, v, c) && precedes(v, c, bv, bi)) {
+          bv = v;
+          bi = c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (precedes(ov, oi, bv, bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        topk_idx[static_cast<size_t>(row0 + warp) * k + j] = bi;
+        if (topk_val != nullptr) topk_val[static_cast<size_t>(row0 + warp) * k + j] = bv;
+      }
+      last_v = bv;
+      last_i = bi;
+    }
+  }
+}
+
 }  // namespace
+
+bool score_fused_supported(int n, int D, int E, int C) {
+  const size_t smem = static_cast<size_t>(RPB) * (D + 2 * E + (C > 0 ? C : 0)) * sizeof(float);
+  return n <= 8192 && smem <= 160 * 1024 && (E % 4) == 0 && (D % 2) == 0;
+}
+
+cudaError_t launch_score_fused(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C,
+                               float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx,
+                               float* topk_val, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const size_t smem = static_cast<size_t>(RPB) * (D + 2 * E + (text_w ? C : 0)) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(score_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  score_fused_kernel<<<(n + RPB - 1) / RPB, 256, smem, stream>>>(feats, n, D, proj, E, text_w, C, scale, k, emb_out,
+                                                                 logits_out, topk_idx, topk_val);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_sgemm(const float* A, const float* B, float* C, int M, int N, int K, float alpha,
                          cudaStream_t stream) {

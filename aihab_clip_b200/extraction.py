@@ -60,24 +60,56 @@ class ShardedExtractor:
     """
 
     def __init__(self, model, head: ZeroShotHead, batch_size: int = 128, device: Optional[torch.device] = None,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, copy_results_to_host: bool = False):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, copy_results_to_host: bool = False,
+                 step_fn: Optional[Callable] = None):
         import torch.distributed as dist
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.rank = rank if rank is not None else (self.dist.get_rank() if self.dist else 0)
         self.world = world_size if world_size is not None else (self.dist.get_world_size() if self.dist else 1)
         self.model, self.head, self.batch = model, head, int(batch_size)
-        self.device = device or model.visual.proj.device
+        self.device = torch.device(device) if device is not None else model.visual.proj.device
         self.copy_results_to_host = copy_results_to_host
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        # step_fn(images) -> (emb [n,E] fp32, idx [n,1] int64) replaces the CUDA path; it exists so that the
+        # sharding / packing / gather logic can be exercised by world_size-2 gloo tests on a CPU-only box
+        self._step_fn = step_fn
         if self.device.type != "cuda":
-            raise RuntimeError("ShardedExtractor needs the model on a CUDA device (no CPU fallback)")
-        self._copy_stream = torch.cuda.Stream(self.device)
-        self._out_stream = torch.cuda.Stream(self.device)
+            if step_fn is None:
+                raise RuntimeError("ShardedExtractor needs the model on a CUDA device (no CPU fallback)")
+            self._copy_stream = self._out_stream = None
+        else:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._out_stream = torch.cuda.Stream(self.device)
+
+    def _step(self, images):
+        if self._step_fn is not None:
+            return self._step_fn(images)
+        emb, _, idx = encode_and_score(self.model, images, self.head, 1)
+        return emb, idx
+
+    def _gather(self, packed, per, n_total):
+        full = torch.empty(per * self.world, packed.shape[1], dtype=torch.float32, device=packed.device)
+        self.dist.all_gather_into_tensor(full, packed)  # the ONLY collective of the path (NCCL over NVLink)
+        return full[:n_total]
+
+    def _run_host(self, source, n_total, gather):
+        """Synchronous CPU variant of run() used with step_fn (tests)."""
+        lo, hi, per = shard_range(n_total, self.rank, self.world)
+        E = self.head.proj.shape[1]
+        packed = torch.zeros(per, E + 1, dtype=torch.float32)
+        for b0 in range(lo, hi, self.batch):
+            emb, idx = self._step(source(b0, min(hi, b0 + self.batch)))
+            packed[b0 - lo:b0 - lo + emb.shape[0], :E] = emb
+            packed[b0 - lo:b0 - lo + emb.shape[0], E] = idx[:, 0].to(torch.float32)
+        full = self._gather(packed, per, n_total) if (gather and self.world > 1) else packed[:hi - lo]
+        return {"features": full[:, :E], "preds": full[:, E].to(torch.int64), "host_copy": None, "range": (lo, hi)}
 
     def run(self, source: Callable[[int, int], torch.Tensor], n_total: int, gather: bool = True):
         """Returns dict(features [N,E] fp32 normalised, preds [N] int64) — gathered over all ranks when ``gather``
         (identical on every rank), else this rank's shard only."""
+        if self.device.type != "cuda":
+            return self._run_host(source, n_total, gather)
         lo, hi, per = shard_range(n_total, self.rank, self.world)
         E = self.head.proj.shape[1]
         dev = self.device
@@ -107,7 +139,7 @@ class ShardedExtractor:
             nxt = stage(i + 1) if i + 1 < len(starts) else None  # copy of batch i+1 overlaps compute of batch i
             if ev is not None:
                 compute.wait_event(ev)
-            emb, _, idx = encode_and_score(self.model, cur, self.head, 1)
+            emb, idx = self._step(cur)
             cur.record_stream(compute)
             n = emb.shape[0]
             row0 = b0 - lo
@@ -125,9 +157,7 @@ class ShardedExtractor:
         if gather and self.world > 1:
             if self.dist is None:
                 raise RuntimeError("world_size > 1 needs an initialised torch.distributed process group")
-            full = torch.empty(per * self.world, E + 1, dtype=torch.float32, device=dev)
-            self.dist.all_gather_into_tensor(full, packed)  # the ONLY collective of the path (NCCL over NVLink)
-            full = full[:n_total]
+            full = self._gather(packed, per, n_total)
         else:
             full = packed[:hi - lo]
         return {"features": full[:, :E], "preds": full[:, E].to(torch.int64), "host_copy": host_out,

@@ -142,7 +142,8 @@ def test_preprocess_bit_exact(cuda_device, gold, meta):
     assert torch.equal(y16, y32.half())
 
 
-@pytest.mark.parametrize("n,D,E,Cn,k", [(64, 768, 512, 20, 3), (1000, 768, 512, 1000, 5), (5, 128, 64, 18, 1)])
+@pytest.mark.parametrize("n,D,E,Cn,k", [(64, 768, 512, 20, 3), (1000, 768, 512, 1000, 5), (5, 128, 64, 18, 1),
+                                        (9000, 768, 512, 100, 5)])
 def test_score_matches_oracle(cuda_device, n, D, E, Cn, k):
     _lib, ops = _ops()
     rng = np.random.default_rng(n + Cn)
