@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -254,6 +255,8 @@ struct aihab_vit {
   void* y = nullptr;        // [cap_rows, D] 16-bit (LN output / attention output)
   void* big = nullptr;      // [cap_rows, 4D] 16-bit (qkv [.,3D] and MLP hidden [.,4D] share it)
   CUtensorMap m_patches, m_y, m_h, m_x;  // m_x: fp32 residual stream, {32,32} boxes (EPI_BIAS_RES_32)
+  CUtensorMap m_attn_q, m_attn_kv;       // qkv view [cap_rows, 3D] of `big` for the tcgen05 attention
+  bool attn_tc = false;
   size_t ws_bytes = 0;
   std::vector<void*> allocs;
 };
@@ -345,7 +348,10 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
     if (run_gemm(h, h->m_y, b.m_in, M, 3 * D, D, aihab::EPI_BIAS_16, b.b_in, h->big, nullptr, 3 * D, s)) return 1;
     {
       ProfScope ps(PC_ATTN, 4.0 * n * L * L * D, s);
-      CKL(aihab::launch_attention(h->big, h->y, n, L, h->cfg.heads, h->bf16, s));
+      if (h->attn_tc)
+        CKL(aihab::launch_attention_tc(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, s));
+      else
+        CKL(aihab::launch_attention(h->big, h->y, n, L, h->cfg.heads, h->bf16, s));
     }
     if (run_gemm(h, h->m_y, b.m_out, M, D, D, aihab::EPI_BIAS_RES_32, b.b_out, nullptr, h->x, D, s)) return 1;
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))   (clip/model.py:171-175,185)
@@ -505,6 +511,16 @@ int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, in
       aihab::make_tmap_2d_f32_box32(&h->m_x, h->x, h->cap_rows, D, static_cast<uint64_t>(D) * 4) != cudaSuccess) {
     fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the workspace");
     return bail(1);
+  }
+  h->attn_tc = aihab::attention_tc_supported(L) && getenv("AIHAB_ATTN_LEGACY") == nullptr;
+  if (h->attn_tc) {
+    const uint64_t pitch = static_cast<uint64_t>(3 * D) * 2;
+    if (aihab::make_tmap_2d_16bit(&h->m_attn_q, h->big, h->cap_rows, 3 * D, pitch, 128, h->bf16) != cudaSuccess ||
+        aihab::make_tmap_2d_16bit(&h->m_attn_kv, h->big, h->cap_rows, 3 * D, pitch, aihab::attention_tc_key_rows(L),
+                                  h->bf16) != cudaSuccess) {
+      fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the attention views");
+      return bail(1);
+    }
   }
   CK(cudaDeviceSynchronize());
   *out = h;
@@ -678,6 +694,17 @@ int aihab_attention(const void* qkv, void* out, int n, int L, int H, int dtype, 
   if (qkv == nullptr || out == nullptr || n < 0) return fail("aihab_attention: bad argument");
   if (dtype != AIHAB_F16 && dtype != AIHAB_BF16) return fail("aihab_attention: dtype must be AIHAB_F16 or AIHAB_BF16");
   DeviceGuard guard(device_of(qkv));
+  if (n == 0) return 0;
+  if (aihab::attention_tc_supported(L) && getenv("AIHAB_ATTN_LEGACY") == nullptr) {
+    CUtensorMap mq, mkv;
+    const int bf16 = dtype == AIHAB_BF16;
+    const uint64_t rows = static_cast<uint64_t>(n) * L, pitch = static_cast<uint64_t>(3 * H * 64) * 2;
+    CK(aihab::gemm_init());
+    CK(aihab::make_tmap_2d_16bit(&mq, qkv, rows, 3 * H * 64, pitch, 128, bf16));
+    CK(aihab::make_tmap_2d_16bit(&mkv, qkv, rows, 3 * H * 64, pitch, aihab::attention_tc_key_rows(L), bf16));
+    CKL(aihab::launch_attention_tc(mq, mkv, out, n, L, H, bf16, static_cast<cudaStream_t>(stream)));
+    return 0;
+  }
   CKL(aihab::launch_attention(qkv, out, n, L, H, dtype == AIHAB_BF16, static_cast<cudaStream_t>(stream)));
   return 0;
 }

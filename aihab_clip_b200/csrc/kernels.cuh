@@ -1,5 +1,6 @@
 // Launchers for the non-GEMM kernels of the hot path (all sm_100a, all on a caller-supplied stream).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,6 +29,14 @@ cudaError_t launch_im2col(const void* images, int in_dtype, int n, int R, int p,
 //   out : [N*L, D] 16-bit
 cudaError_t launch_attention(const void* qkv, void* out, int n_img, int L, int H, int is_bf16, cudaStream_t stream);
 cudaError_t attention_init(int max_L);
+
+// tcgen05 / TMEM variant for 64 < L <= 256 (ViT-B/16's 197 tokens): S and O live in TMEM, softmax reads S with
+// tcgen05.ld.  tmap_q: make_tmap_2d_16bit over qkv [n*L, 3D] with a 128-row box; tmap_kv: same matrix with an
+// attention_tc_key_rows(L)-row box.
+bool attention_tc_supported(int L);
+int attention_tc_key_rows(int L);
+cudaError_t launch_attention_tc(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
+                                int H, int is_bf16, cudaStream_t stream);
 
 // fp32 -> 16-bit cast of a weight matrix [rows, cols] into [rows, cols_pad] (zero padded columns).
 cudaError_t launch_cast_pad(const float* src, int rows, int cols, void* dst, int cols_pad, int out_bf16,

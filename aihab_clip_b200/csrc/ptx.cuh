@@ -143,6 +143,21 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -161,10 +176,16 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same 128 B-row SWIZZLE_128B tile read as an MN-major operand (the contiguous 64 elements of a row run along M/N,
+// rows run along K): 8-row K groups are SBO = 1024 B apart; LBO (next 64 M/N elements) is unused for M/N = 64.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  return make_kmajor_sw128_desc(smem_addr);  // identical field values; the major-ness lives in the instr descriptor
+}
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
 //   ab_format: 0 = fp16, 1 = bf16.
-__host__ __device__ constexpr uint32_t make_idesc_f16(int ab_format, int umma_m, int umma_n) {
+__host__ __device__ constexpr uint32_t make_idesc_f16(int ab_format, int umma_m, int umma_n, int b_mn_major = 0) {
   return (1u << 4)                                     // c_format = F32
+         | (static_cast<uint32_t>(b_mn_major) << 16)   // b_major: 0 = K-major, 1 = MN-major
          | (static_cast<uint32_t>(ab_format) << 7)     // a_format
          | (static_cast<uint32_t>(ab_format) << 10)    // b_format
          | (static_cast<uint32_t>(umma_n >> 3) << 17)  // N >> 3

@@ -107,7 +107,8 @@ def test_layernorm(cuda_device, D, out_dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("L,H,n", [(50, 12, 3), (197, 12, 2), (257, 16, 2), (577, 16, 1), (17, 2, 4), (64, 1, 1)])
+@pytest.mark.parametrize("L,H,n", [(50, 12, 3), (197, 12, 2), (257, 16, 2), (577, 16, 1), (17, 2, 4), (64, 1, 1),
+                                   (256, 4, 2), (100, 2, 3), (129, 2, 2), (65, 1, 5), (197, 12, 9)])
 def test_attention(cuda_device, dtype, L, H, n):
     _lib, ops = _ops()
     rng = np.random.default_rng(L + H)
