@@ -83,6 +83,19 @@ int fail(const std::string& msg) {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// attention kernel choice: 2 = persistent tcgen05 (L <= 224), 1 = tcgen05 (L <= 256), 0 = mma.sync (any L <= 908).
+// AIHAB_ATTN=legacy|tc|tcp caps the choice (A/B measurements); default picks the fastest supported kernel.
+int attention_kind(int L) {
+  int cap = 2;
+  if (const char* e = getenv("AIHAB_ATTN")) {
+    if (!strcmp(e, "legacy")) cap = 0;
+    else if (!strcmp(e, "tc")) cap = 1;
+  }
+  if (cap >= 2 && aihab::attention_tcp_supported(L)) return 2;
+  if (cap >= 1 && aihab::attention_tc_supported(L)) return 1;
+  return 0;
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
@@ -256,7 +269,7 @@ struct aihab_vit {
   void* big = nullptr;      // [cap_rows, 4D] 16-bit (qkv [.,3D] and MLP hidden [.,4D] share it)
   CUtensorMap m_patches, m_y, m_h, m_x;  // m_x: fp32 residual stream, {32,32} boxes (EPI_BIAS_RES_32)
   CUtensorMap m_attn_q, m_attn_kv;       // qkv view [cap_rows, 3D] of `big` for the tcgen05 attention
-  bool attn_tc = false;
+  int attn_kind = 0;
   size_t ws_bytes = 0;
   std::vector<void*> allocs;
 };
@@ -348,7 +361,9 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
     if (run_gemm(h, h->m_y, b.m_in, M, 3 * D, D, aihab::EPI_BIAS_16, b.b_in, h->big, nullptr, 3 * D, s)) return 1;
     {
       ProfScope ps(PC_ATTN, 4.0 * n * L * L * D, s);
-      if (h->attn_tc)
+      if (h->attn_kind == 2)
+        CKL(aihab::launch_attention_tcp(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, h->num_sms, s));
+      else if (h->attn_kind == 1)
         CKL(aihab::launch_attention_tc(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, s));
       else
         CKL(aihab::launch_attention(h->big, h->y, n, L, h->cfg.heads, h->bf16, s));
@@ -512,8 +527,8 @@ int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, in
     fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the workspace");
     return bail(1);
   }
-  h->attn_tc = aihab::attention_tc_supported(L) && getenv("AIHAB_ATTN_LEGACY") == nullptr;
-  if (h->attn_tc) {
+  h->attn_kind = attention_kind(L);
+  if (h->attn_kind > 0) {
     const uint64_t pitch = static_cast<uint64_t>(3 * D) * 2;
     if (aihab::make_tmap_2d_16bit(&h->m_attn_q, h->big, h->cap_rows, 3 * D, pitch, 128, h->bf16) != cudaSuccess ||
         aihab::make_tmap_2d_16bit(&h->m_attn_kv, h->big, h->cap_rows, 3 * D, pitch, aihab::attention_tc_key_rows(L),
@@ -695,14 +710,18 @@ int aihab_attention(const void* qkv, void* out, int n, int L, int H, int dtype, 
   if (dtype != AIHAB_F16 && dtype != AIHAB_BF16) return fail("aihab_attention: dtype must be AIHAB_F16 or AIHAB_BF16");
   DeviceGuard guard(device_of(qkv));
   if (n == 0) return 0;
-  if (aihab::attention_tc_supported(L) && getenv("AIHAB_ATTN_LEGACY") == nullptr) {
+  const int kind = attention_kind(L);
+  if (kind > 0) {
     CUtensorMap mq, mkv;
     const int bf16 = dtype == AIHAB_BF16;
     const uint64_t rows = static_cast<uint64_t>(n) * L, pitch = static_cast<uint64_t>(3 * H * 64) * 2;
     CK(aihab::gemm_init());
     CK(aihab::make_tmap_2d_16bit(&mq, qkv, rows, 3 * H * 64, pitch, 128, bf16));
     CK(aihab::make_tmap_2d_16bit(&mkv, qkv, rows, 3 * H * 64, pitch, aihab::attention_tc_key_rows(L), bf16));
-    CKL(aihab::launch_attention_tc(mq, mkv, out, n, L, H, bf16, static_cast<cudaStream_t>(stream)));
+    if (kind == 2)
+      CKL(aihab::launch_attention_tcp(mq, mkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream)));
+    else
+      CKL(aihab::launch_attention_tc(mq, mkv, out, n, L, H, bf16, static_cast<cudaStream_t>(stream)));
     return 0;
   }
   CKL(aihab::launch_attention(qkv, out, n, L, H, dtype == AIHAB_BF16, static_cast<cudaStream_t>(stream)));

@@ -1,0 +1,329 @@
+// Persistent, software-pipelined tcgen05 / TMEM attention for 64 < L <= 224 (ViT-B/16: L = 197, Lk = 208).
+// One CTA per SM walks a static list of work items (image, head, 128-query tile):
+//   warp 0 (lane 0)  TMA producer : Q [128x64], K [Lk x 64], V [Lk x 64] of item i+1 land in the other smem stage
+//                                   while item i is in its softmax
+//   warp 1 (lane 0)  MMA issuer   : S(i+1) = Q K^T is issued into the other TMEM S buffer BEFORE it waits for P(i), so
+//                                   the softmax warps never wait for a QK^T; then O = P(i) V (V read as an MN-major
+//                                   operand straight from its [key][d] tile)
+//   warps 2..9       softmax      : two threads per query row; pass 1 row max, pass 2 exp2 / row sum / P -> smem in the
+//                                   UMMA K-major SWIZZLE_128B layout; the O(i-1) epilogue (TMEM -> 1/sum -> global) runs
+//                                   between P(i) and the hand-off, hiding the PV MMA of the previous item
+// TMEM: S0 [0,224) S1 [224,448) O [448,512).  smem: 2 x (Q 16 KB + K 28 KB + V 28 KB) + P 64 KB = 208 KB.
+// Reference: clip/model.py:179-181 (nn.MultiheadAttention core: softmax(q k^T / sqrt(64)) v, no mask).
+#include "gemm_tcgen05.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace aihab {
+
+namespace {
+
+constexpr int P_THREADS = 320;
+constexpr int KV_MAX = 224;
+constexpr int ST_Q = 0;
+constexpr int ST_K = 16384;
+constexpr int ST_V = ST_K + KV_MAX * 128;
+constexpr int ST_BYTES = ST_V + KV_MAX * 128;  // 73728
+constexpr int OFF_P = 2 * ST_BYTES;            // 64 KB: 4 key blocks x (128 rows x 128 B)
+constexpr int OFF_BAR = OFF_P + 65536;
+constexpr int OFF_RED = OFF_BAR + 128;         // s_max[2][256], s_sum[2][256]
+constexpr int P_SMEM = OFF_RED + 4096 + 1024;
+constexpr int TM_S = 224;                      // TMEM columns per S buffer
+constexpr int TM_O = 448;
+static_assert(ST_K % 1024 == 0 && ST_V % 1024 == 0 && ST_BYTES % 1024 == 0, "SWIZZLE_128B tiles need 1024 B alignment");
+static_assert(P_SMEM <= 227 * 1024, "smem budget");
+
+// Softmax of one query row half for one item, fully unrolled over NC 16-column chunks: the S values are read from
+// TMEM ONCE (NC x tcgen05.ld.x16 in flight together) and stay in registers across the row-max exchange.
+// Columns >= L are masked; only the last two chunks of a thread's range can contain such columns.
+template <bool BF16, int NC>
+__device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L, float sl2, float* s_max_b,
+                                             float* s_sum_b, int half, int row, uint8_t* prow, bool has_rows,
+                                             uint64_t* bar_o, int wait_o_parity) {
+  uint32_t r[NC][16];
+  if (has_rows) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) ptx::tmem_ld_32x16(t_row + (c_begin + i) * 16, r[i]);
+    ptx::tmem_ld_wait();
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      if (i < NC - 2) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          m0 = fmaxf(m0, __uint_as_float(r[i][j]));
+          m1 = fmaxf(m1, __uint_as_float(r[i][j + 1]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if ((c_begin + i) * 16 + j < L) m0 = fmaxf(m0, __uint_as_float(r[i][j]));
+      }
+    }
+    s_max_b[half * 128 + row] = fmaxf(m0, m1);
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (wait_o_parity >= 0) {  // PV of the previous item complete: the P buffer is free and its O is ready
+    ptx::mbar_wait(bar_o, static_cast<uint32_t>(wait_o_parity));
+    ptx::tc_fence_after();
+  }
+  if (has_rows) {
+    const float ms = fmaxf(s_max_b[row], s_max_b[128 + row]) * sl2;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int c = c_begin + i;
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[i][2 * j]), sl2, -ms));
+        float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[i][2 * j + 1]), sl2, -ms));
+        if (i >= NC - 2) {
+          if (c * 16 + 2 * j >= L) p0 = 0.f;
+          if (c * 16 + 2 * j + 1 >= L) p1 = 0.f;
+        }
+        l0 += p0;
+        l1 += p1;
+        pk[j] = ptx::pack2<BF16>(p0, p1);
+      }
+      uint8_t* blk = prow + (c >> 2) * 16384;  // 16 keys = two 16 B units of the row in key block c / 4
+      const int u = (c & 3) * 2;
+      *reinterpret_cast<uint4*>(blk + (((u) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(blk + (((u + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    s_sum_b[half * 128 + row] = l0 + l1;
+  }
+}
+
+template <bool BF16, int NC>
+__global__ void __launch_bounds__(P_THREADS, 1)
+attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                     uint16_t* __restrict__ out, int L, int H, int Lk, int nq, int total) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* bar_qk = bars + 0;      // [2] Q + K of a stage landed
+  uint64_t* bar_v = bars + 2;       // [2] V of a stage landed
+  uint64_t* bar_stfree = bars + 4;  // [2] stage inputs consumed (commit after PV)
+  uint64_t* bar_sfull = bars + 6;   // [2] S buffer written
+  uint64_t* bar_sfree = bars + 8;   // [2] S buffer read by all softmax threads
+  uint64_t* bar_p = bars + 10;      // P written (and O of the previous item read)
+  uint64_t* bar_o = bars + 11;      // O written (P and the stage are free again)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* s_max = reinterpret_cast<float*>(smem + OFF_RED);  // [2][256]
+  float* s_sum = s_max + 512;                               // [2][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  const int D = H * 64;
+  const int n_items = blockIdx.x < total ? (total - static_cast<int>(blockIdx.x) + G - 1) / G : 0;
+
+  // item it of this CTA -> (image, head, query tile).  For two query tiles per head the tile parity alternates
+  // with `it` so that every CTA sees the same mix of full (128-row) and partial tiles (G is even).
+  auto decode = [&](int it, int& img, int& h, int& qt) {
+    const int idx = static_cast<int>(blockIdx.x) + it * G;
+    int u = idx;
+    qt = 0;
+    if (nq == 2) {
+      u = idx >> 1;
+      qt = (idx & 1) ^ (it & 1);
+    }
+    img = u / H;
+    h = u - img * H;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmap_q);
+      ptx::prefetch_tmap(&tmap_kv);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&bar_qk[i], 1);
+        ptx::mbar_init(&bar_v[i], 1);
+        ptx::mbar_init(&bar_stfree[i], 1);
+        ptx::mbar_init(&bar_sfull[i], 1);
+        ptx::mbar_init(&bar_sfree[i], 256);
+      }
+      ptx::mbar_init(bar_p, 256);
+      ptx::mbar_init(bar_o, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < n_items; ++it) {
+        int img, h, qt;
+        decode(it, img, h, qt);
+        const int s = it & 1, k = it >> 1;
+        uint8_t* st = smem + s * ST_BYTES;
+        if (it >= 2) ptx::mbar_wait(&bar_stfree[s], (k - 1) & 1);
+        const int row0 = img * L;
+        ptx::mbar_expect_tx(&bar_qk[s], 128 * 128 + Lk * 128);
+        ptx::tma_load_2d(st + ST_Q, &tmap_q, &bar_qk[s], h * 64, row0 + qt * 128);
+        ptx::tma_load_2d(st + ST_K, &tmap_kv, &bar_qk[s], D + h * 64, row0);
+        ptx::mbar_expect_tx(&bar_v[s], Lk * 128);
+        ptx::tma_load_2d(st + ST_V, &tmap_kv, &bar_v[s], 2 * D + h * 64, row0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::make_idesc_f16(BF16 ? 1 : 0, 128, Lk);
+      const uint32_t idesc_o = ptx::make_idesc_f16(BF16 ? 1 : 0, 128, 64, /*b_mn_major=*/1);
+      const uint32_t p_base = ptx::smem_u32(smem + OFF_P);
+      const int ksteps = Lk >> 4;
+      auto issue_s = [&](int it) {
+        const int s = it & 1, k = it >> 1;
+        ptx::mbar_wait(&bar_qk[s], k & 1);
+        if (it >= 2) ptx::mbar_wait(&bar_sfree[s], (k - 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t st = ptx::smem_u32(smem + s * ST_BYTES);
+        const uint64_t qd = ptx::make_kmajor_sw128_desc(st + ST_Q);
+        const uint64_t kd = ptx::make_kmajor_sw128_desc(st + ST_K);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + s * TM_S, qd + 2 * kk, kd + 2 * kk, idesc_s, kk != 0);
+        ptx::umma_commit(&bar_sfull[s]);
+      };
+      if (n_items > 0) issue_s(0);
+      for (int it = 0; it < n_items; ++it) {
+        if (it + 1 < n_items) issue_s(it + 1);
+        const int s = it & 1, k = it >> 1;
+        ptx::mbar_wait(bar_p, it & 1);
+        ptx::mbar_wait(&bar_v[s], k & 1);
+        ptx::tc_fence_after();
+        const uint32_t v_base = ptx::smem_u32(smem + s * ST_BYTES + ST_V);
+        for (int j = 0; j < ksteps; ++j) {
+          const uint64_t pd = ptx::make_kmajor_sw128_desc(p_base + (j >> 2) * 16384 + (j & 3) * 32);
+          const uint64_t vd = ptx::make_mnmajor_sw128_desc(v_base + j * 2048);
+          ptx::umma_f16(tmem + TM_O, pd, vd, idesc_o, j != 0);
+        }
+        ptx::umma_commit(bar_o);
+        ptx::umma_commit(&bar_stfree[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue (warps 2..9)
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const float sl2 = 0.125f * 1.4426950408889634f;
+    // NC = ceil(Lk / 32) 16-column chunks per thread (3..7); a chunk past Lk is fully masked
+    const int c_begin = half * NC;
+    uint8_t* prow = smem + OFF_P + row * 128;
+
+    // O(prev) -> global: this thread owns 32 of the 64 output columns of its row
+    auto epilogue = [&](int img, int h, int qt, int b) {
+      if (qt * 128 + quad * 32 >= L) return;
+      uint32_t o[32];
+      ptx::tmem_ld_32x32(tmem + lane_off + TM_O + half * 32, o);
+      ptx::tmem_ld_wait();
+      const int grow = qt * 128 + row;
+      if (grow < L) {
+        const float inv_l = 1.0f / (s_sum[b * 256 + row] + s_sum[b * 256 + 128 + row]);
+        uint16_t* dst = out + (static_cast<size_t>(img) * L + grow) * D + h * 64 + half * 32;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 v;
+          v.x = ptx::pack2<BF16>(__uint_as_float(o[8 * u]) * inv_l, __uint_as_float(o[8 * u + 1]) * inv_l);
+          v.y = ptx::pack2<BF16>(__uint_as_float(o[8 * u + 2]) * inv_l, __uint_as_float(o[8 * u + 3]) * inv_l);
+          v.z = ptx::pack2<BF16>(__uint_as_float(o[8 * u + 4]) * inv_l, __uint_as_float(o[8 * u + 5]) * inv_l);
+          v.w = ptx::pack2<BF16>(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + 8 * u) = v;
+        }
+      }
+    };
+
+    int p_img = 0, p_h = 0, p_qt = 0;
+    for (int it = 0; it < n_items; ++it) {
+      int img, h, qt;
+      decode(it, img, h, qt);
+      const int b = it & 1, k = it >> 1;
+      const bool has_rows = qt * 128 + quad * 32 < L;
+      const uint32_t t_row = tmem + lane_off + b * TM_S;
+
+      ptx::mbar_wait(&bar_sfull[b], k & 1);
+      ptx::tc_fence_after();
+      const int wait_o = it > 0 ? ((it - 1) & 1) : -1;
+      float* smb = s_max + b * 256;
+      float* ssb = s_sum + b * 256;
+      softmax_item<BF16, NC>(t_row, c_begin, L, sl2, smb, ssb, half, row, prow, has_rows, bar_o, wait_o);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_sfree[b]);           // S buffer b may be overwritten by S(it+2)
+      if (it > 0) epilogue(p_img, p_h, p_qt, b ^ 1);
+      ptx::tc_fence_before();                    // O(it-1) read (wait::ld inside) before PV(it) overwrites it
+      ptx::fence_proxy_async();                  // P stores -> visible to the MMA's async-proxy reads
+      ptx::mbar_arrive(bar_p);
+      p_img = img;
+      p_h = h;
+      p_qt = qt;
+    }
+    if (n_items > 0) {
+      ptx::mbar_wait(bar_o, (n_items - 1) & 1);
+      ptx::tc_fence_after();
+      epilogue(p_img, p_h, p_qt, (n_items - 1) & 1);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+template <bool BF16, int NC>
+cudaError_t launch_nc(const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* out, int L, int H, int Lk, int nq,
+                      int total, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tcp_kernel<BF16, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  attention_tcp_kernel<BF16, NC><<<grid, P_THREADS, P_SMEM, stream>>>(tq, tkv, out, L, H, Lk, nq, total);
+  return cudaGetLastError();
+}
+
+template <bool BF16>
+cudaError_t launch_dt(int nc, const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* out, int L, int H, int Lk,
+                      int nq, int total, int grid, cudaStream_t stream) {
+  switch (nc) {
+    case 3: return launch_nc<BF16, 3>(tq, tkv, out, L, H, Lk, nq, total, grid, stream);
+    case 4: return launch_nc<BF16, 4>(tq, tkv, out, L, H, Lk, nq, total, grid, stream);
+    case 5: return launch_nc<BF16, 5>(tq, tkv, out, L, H, Lk, nq, total, grid, stream);
+    case 6: return launch_nc<BF16, 6>(tq, tkv, out, L, H, Lk, nq, total, grid, stream);
+    case 7: return launch_nc<BF16, 7>(tq, tkv, out, L, H, Lk, nq, total, grid, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace
+
+bool attention_tcp_supported(int L) { return L > 64 && (L + 15) / 16 * 16 <= KV_MAX; }
+
+cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
+                                 int H, int is_bf16, int num_sms, cudaStream_t stream) {
+  if (n_img <= 0) return cudaSuccess;
+  if (!attention_tcp_supported(L)) return cudaErrorInvalidValue;
+  const int Lk = (L + 15) / 16 * 16;
+  const int nq = (L + 127) / 128;
+  const int total = n_img * H * nq;
+  int grid = total < num_sms ? total : num_sms;
+  if (nq == 2) grid &= ~1;  // even: a CTA's items alternate between the full and the partial query tile
+  const int nc = ((Lk >> 4) + 1) >> 1;
+  uint16_t* o = static_cast<uint16_t*>(out);
+  return is_bf16 ? launch_dt<true>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, stream)
+                 : launch_dt<false>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, stream);
+}
+
+}  // namespace aihab
