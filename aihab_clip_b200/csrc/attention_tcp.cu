@@ -5,10 +5,12 @@
 //   warp 1 (lane 0)  MMA issuer   : S(i+1) = Q K^T is issued into the other TMEM S buffer BEFORE it waits for P(i), so
 //                                   the softmax warps never wait for a QK^T; then O = P(i) V (V read as an MN-major
 //                                   operand straight from its [key][d] tile)
-//   warps 2..9       softmax      : two threads per query row; pass 1 row max, pass 2 exp2 / row sum / P -> smem in the
-//                                   UMMA K-major SWIZZLE_128B layout; the O(i-1) epilogue (TMEM -> 1/sum -> global) runs
-//                                   between P(i) and the hand-off, hiding the PV MMA of the previous item
-// TMEM: S0 [0,224) S1 [224,448) O [448,512).  smem: 2 x (Q 16 KB + K 28 KB + V 28 KB) + P 64 KB = 208 KB.
+//   warps 2..9       softmax      : two threads per query row; S is read from TMEM once (registers), row max exchanged
+//                                   through smem, exp2 / row sum, and P is written back INTO TENSOR MEMORY as packed
+//                                   16-bit pairs over the S columns (tcgen05.st) - the PV MMA takes A from TMEM, so P
+//                                   never touches shared memory; the O(i-1) epilogue (TMEM -> 1/sum -> global) runs
+//                                   before the hand-off, hiding the PV MMA of the previous item
+// TMEM: S0/P0 [0,224) S1/P1 [224,448) O [448,512).  smem: 2 x (Q 16 KB + K 28 KB + V 28 KB) = 144 KB.
 // Reference: clip/model.py:179-181 (nn.MultiheadAttention core: softmax(q k^T / sqrt(64)) v, no mask).
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
@@ -24,8 +26,7 @@ constexpr int ST_Q = 0;
 constexpr int ST_K = 16384;
 constexpr int ST_V = ST_K + KV_MAX * 128;
 constexpr int ST_BYTES = ST_V + KV_MAX * 128;  // 73728
-constexpr int OFF_P = 2 * ST_BYTES;            // 64 KB: 4 key blocks x (128 rows x 128 B)
-constexpr int OFF_BAR = OFF_P + 65536;
+constexpr int OFF_BAR = 2 * ST_BYTES;
 constexpr int OFF_RED = OFF_BAR + 128;         // s_max[2][256], s_sum[2][256]
 constexpr int P_SMEM = OFF_RED + 4096 + 1024;
 constexpr int TM_S = 224;                      // TMEM columns per S buffer
@@ -38,8 +39,7 @@ static_assert(P_SMEM <= 227 * 1024, "smem budget");
 // Columns >= L are masked; only the last two chunks of a thread's range can contain such columns.
 template <bool BF16, int NC>
 __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L, float sl2, float* s_max_b,
-                                             float* s_sum_b, int half, int row, uint8_t* prow, bool has_rows,
-                                             uint64_t* bar_o, int wait_o_parity) {
+                                             float* s_sum_b, int half, int row, bool has_rows) {
   uint32_t r[NC][16];
   if (has_rows) {
 #pragma unroll
@@ -62,11 +62,10 @@ __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L,
     }
     s_max_b[half * 128 + row] = fmaxf(m0, m1);
   }
+  // after this barrier every S column of the tile has been read into registers: P may overwrite S in place
+  ptx::tc_fence_before();
   asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (wait_o_parity >= 0) {  // PV of the previous item complete: the P buffer is free and its O is ready
-    ptx::mbar_wait(bar_o, static_cast<uint32_t>(wait_o_parity));
-    ptx::tc_fence_after();
-  }
+  ptx::tc_fence_after();
   if (has_rows) {
     const float ms = fmaxf(s_max_b[row], s_max_b[128 + row]) * sl2;
     float l0 = 0.f, l1 = 0.f;
@@ -86,12 +85,10 @@ __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L,
         l1 += p1;
         pk[j] = ptx::pack2<BF16>(p0, p1);
       }
-      uint8_t* blk = prow + (c >> 2) * 16384;  // 16 keys = two 16 B units of the row in key block c / 4
-      const int u = (c & 3) * 2;
-      *reinterpret_cast<uint4*>(blk + (((u) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(blk + (((u + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      ptx::tmem_st_32x8(t_row + c * 8, pk);  // 16 keys -> 8 packed columns of P, over the S buffer
     }
     s_sum_b[half * 128 + row] = l0 + l1;
+    ptx::tmem_st_wait();
   }
 }
 
@@ -106,9 +103,9 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* bar_v = bars + 2;       // [2] V of a stage landed
   uint64_t* bar_stfree = bars + 4;  // [2] stage inputs consumed (commit after PV)
   uint64_t* bar_sfull = bars + 6;   // [2] S buffer written
-  uint64_t* bar_sfree = bars + 8;   // [2] S buffer read by all softmax threads
-  uint64_t* bar_p = bars + 10;      // P written (and O of the previous item read)
-  uint64_t* bar_o = bars + 11;      // O written (P and the stage are free again)
+  uint64_t* bar_pvdone = bars + 8;  // [2] PV MMA of the item using S/P buffer b retired: the buffer is free
+  uint64_t* bar_p = bars + 10;      // P written to TMEM (and O of the previous item read)
+  uint64_t* bar_o = bars + 11;      // O written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   float* s_max = reinterpret_cast<float*>(smem + OFF_RED);  // [2][256]
   float* s_sum = s_max + 512;                               // [2][256]
@@ -141,7 +138,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         ptx::mbar_init(&bar_v[i], 1);
         ptx::mbar_init(&bar_stfree[i], 1);
         ptx::mbar_init(&bar_sfull[i], 1);
-        ptx::mbar_init(&bar_sfree[i], 256);
+        ptx::mbar_init(&bar_pvdone[i], 1);
       }
       ptx::mbar_init(bar_p, 256);
       ptx::mbar_init(bar_o, 1);
@@ -178,12 +175,11 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (lane == 0) {
       const uint32_t idesc_s = ptx::make_idesc_f16(BF16 ? 1 : 0, 128, Lk);
       const uint32_t idesc_o = ptx::make_idesc_f16(BF16 ? 1 : 0, 128, 64, /*b_mn_major=*/1);
-      const uint32_t p_base = ptx::smem_u32(smem + OFF_P);
       const int ksteps = Lk >> 4;
       auto issue_s = [&](int it) {
         const int s = it & 1, k = it >> 1;
         ptx::mbar_wait(&bar_qk[s], k & 1);
-        if (it >= 2) ptx::mbar_wait(&bar_sfree[s], (k - 1) & 1);
+        if (it >= 2) ptx::mbar_wait(&bar_pvdone[s], (k - 1) & 1);  // P(it-2) lives in this buffer until PV(it-2) retires
         ptx::tc_fence_after();
         const uint32_t st = ptx::smem_u32(smem + s * ST_BYTES);
         const uint64_t qd = ptx::make_kmajor_sw128_desc(st + ST_Q);
@@ -201,12 +197,12 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         ptx::tc_fence_after();
         const uint32_t v_base = ptx::smem_u32(smem + s * ST_BYTES + ST_V);
         for (int j = 0; j < ksteps; ++j) {
-          const uint64_t pd = ptx::make_kmajor_sw128_desc(p_base + (j >> 2) * 16384 + (j & 3) * 32);
           const uint64_t vd = ptx::make_mnmajor_sw128_desc(v_base + j * 2048);
-          ptx::umma_f16(tmem + TM_O, pd, vd, idesc_o, j != 0);
+          ptx::umma_f16_ts(tmem + TM_O, tmem + s * TM_S + j * 8, vd, idesc_o, j != 0);  // A = P from TMEM
         }
         ptx::umma_commit(bar_o);
         ptx::umma_commit(&bar_stfree[s]);
+        ptx::umma_commit(&bar_pvdone[s]);
       }
     }
   } else {
@@ -218,7 +214,6 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const float sl2 = 0.125f * 1.4426950408889634f;
     // NC = ceil(Lk / 32) 16-column chunks per thread (3..7); a chunk past Lk is fully masked
     const int c_begin = half * NC;
-    uint8_t* prow = smem + OFF_P + row * 128;
 
     // O(prev) -> global: this thread owns 32 of the 64 output columns of its row
     auto epilogue = [&](int img, int h, int qt, int b) {
@@ -252,16 +247,14 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
       ptx::mbar_wait(&bar_sfull[b], k & 1);
       ptx::tc_fence_after();
-      const int wait_o = it > 0 ? ((it - 1) & 1) : -1;
-      float* smb = s_max + b * 256;
-      float* ssb = s_sum + b * 256;
-      softmax_item<BF16, NC>(t_row, c_begin, L, sl2, smb, ssb, half, row, prow, has_rows, bar_o, wait_o);
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&bar_sfree[b]);           // S buffer b may be overwritten by S(it+2)
-      if (it > 0) epilogue(p_img, p_h, p_qt, b ^ 1);
-      ptx::tc_fence_before();                    // O(it-1) read (wait::ld inside) before PV(it) overwrites it
-      ptx::fence_proxy_async();                  // P stores -> visible to the MMA's async-proxy reads
-      ptx::mbar_arrive(bar_p);
+      softmax_item<BF16, NC>(t_row, c_begin, L, sl2, s_max + b * 256, s_sum + b * 256, half, row, has_rows);
+      if (it > 0) {  // O(it-1): its PV was issued a whole softmax ago
+        ptx::mbar_wait(bar_o, (it - 1) & 1);
+        ptx::tc_fence_after();
+        epilogue(p_img, p_h, p_qt, b ^ 1);
+      }
+      ptx::tc_fence_before();                    // P(it) stored (wait::st) and O(it-1) read (wait::ld) ...
+      ptx::mbar_arrive(bar_p);                   // ... before PV(it) may read P and overwrite O
       p_img = img;
       p_h = h;
       p_qt = qt;
