@@ -52,6 +52,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Polling wait for single-thread roles (TMA producer / MMA issuer) that share an SM sub-partition with compute warps:
+// back off between polls so the spin loop does not eat their issue slots.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {

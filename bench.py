@@ -234,7 +234,7 @@ def run_b200(args):
     # ---------------- timed region 1: device-resident inputs (value) ----------------
     gather_buf = torch.empty(world * B, E + 1, dtype=torch.float32, device=dev) if world > 1 else None
     sampler = ClockSampler(local) if rank == 0 else None
-    _lib.profile_enable(True)
+    _lib.profile_enable(not args.no_kernel_profile)
     for c in _lib.PROFILE_CLASSES:
         _lib.profile_read(c, reset=True)
     barrier()
@@ -368,6 +368,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="--impl reference: images per step (bounded sample)")
     ap.add_argument("--cpu-images", type=int, default=8, help="cpu_baseline sample size per repetition")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-profile", action="store_true",
+                    help="do not record per-launch CUDA events in the timed region (roofline becomes 0)")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_b200(args)
 
