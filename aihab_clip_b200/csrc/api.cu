@@ -13,6 +13,9 @@
 #include <tuple>
 #include <vector>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 
@@ -254,6 +257,8 @@ struct aihab_vit {
     void *w_in = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
     float *b_in = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
     float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    // LayerNorm folded into the consumer GEMM: s_n = sum_k gamma_k W16_nk, b'_n = bias_n + sum_k beta_k W16_nk
+    float *s_in = nullptr, *bp_in = nullptr, *s_fc = nullptr, *bp_fc = nullptr;
     CUtensorMap m_in[2], m_out[2], m_fc[2], m_proj[2];  // [0] = 128-row box, [1] = 256-row box
   };
   std::vector<Block> blocks;
@@ -267,6 +272,10 @@ struct aihab_vit {
   float* x = nullptr;       // [cap_rows, D] fp32 residual stream
   void* y = nullptr;        // [cap_rows, D] 16-bit (LN output / attention output)
   void* big = nullptr;      // [cap_rows, 4D] 16-bit (qkv [.,3D] and MLP hidden [.,4D] share it)
+  void* y2 = nullptr;       // [cap_rows, D] 16-bit: gamma * x written by the residual epilogues (LayerNorm fold)
+  float* ln_stats = nullptr;  // [cap_rows, kMaxStatBlocks, 2] per-tile (sum, sum sq) partials of the residual rows
+  bool ln_fold = true;
+  CUtensorMap m_y2;
   CUtensorMap m_patches, m_y, m_h, m_x;  // m_x: fp32 residual stream, {32,32} boxes (EPI_BIAS_RES_32)
   CUtensorMap m_attn_q, m_attn_kv;       // qkv view [cap_rows, 3D] of `big` for the tcgen05 attention
   int attn_kind = 0;
@@ -312,15 +321,55 @@ int upload_16(aihab_vit* h, const float* src, int rows, int cols, int cols_pad, 
   return 0;
 }
 
+// LayerNorm fold constants for a consumer Linear W [N, K] fed by LayerNorm(gamma, beta):
+//   s[n] = sum_k gamma[k] * W16[n][k],   bp[n] = bias[n] + sum_k beta[k] * W16[n][k]
+// with W16 = W rounded to the tensor-core operand format actually multiplied.  Pointers may be host or device.
+int fold_ln(aihab_vit* h, const float* W, const float* bias, const float* gamma, const float* beta, int N, int K,
+            float** s_out, float** bp_out) {
+  std::vector<float> w(static_cast<size_t>(N) * K), b(N), g(K), be(K), sv(N), bp(N);
+  CK(cudaMemcpy(w.data(), W, w.size() * sizeof(float), cudaMemcpyDefault));
+  CK(cudaMemcpy(b.data(), bias, N * sizeof(float), cudaMemcpyDefault));
+  CK(cudaMemcpy(g.data(), gamma, K * sizeof(float), cudaMemcpyDefault));
+  CK(cudaMemcpy(be.data(), beta, K * sizeof(float), cudaMemcpyDefault));
+  for (int n = 0; n < N; ++n) {
+    double acc_s = 0.0, acc_b = 0.0;
+    const float* row = w.data() + static_cast<size_t>(n) * K;
+    for (int k = 0; k < K; ++k) {
+      const float w16 = h->bf16 ? __bfloat162float(__float2bfloat16_rn(row[k])) : __half2float(__float2half_rn(row[k]));
+      acc_s += static_cast<double>(g[k]) * w16;
+      acc_b += static_cast<double>(be[k]) * w16;
+    }
+    sv[n] = static_cast<float>(acc_s);
+    bp[n] = static_cast<float>(static_cast<double>(b[n]) + acc_b);
+  }
+  if (upload_f32(h, sv.data(), N, s_out) || upload_f32(h, bp.data(), N, bp_out)) return 1;
+  return 0;
+}
+
 int weight_maps(aihab_vit* h, const void* w, int N, int K, CUtensorMap (&m)[2]) {
   CK(aihab::make_tmap_2d_16bit(&m[0], w, N, K, static_cast<uint64_t>(K) * 2, 128, h->bf16));
   CK(aihab::make_tmap_2d_16bit(&m[1], w, N, K, static_cast<uint64_t>(K) * 2, 256, h->bf16));
   return 0;
 }
 
+constexpr int kMaxStatBlocks = 8;  // N / 128 for N <= 1024
+
+struct LnOpt {
+  const float* gamma = nullptr;  // producer: gamma of the next LayerNorm -> y2 / ln_stats are written
+  const float* s = nullptr;      // consumer: s_n; statistics are read from ln_stats
+  int nsb = 0;                   // consumer: stat blocks per row written by the producer
+};
+
 int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], int M, int N, int K, int epi,
-             const float* bias, void* out16, float* out32, int ldo, cudaStream_t s) {
+             const float* bias, void* out16, float* out32, int ldo, cudaStream_t s, const LnOpt& ln = LnOpt(),
+             int* n_blocks_out = nullptr) {
   aihab::GemmParams p{};
+  p.ln_gamma = ln.gamma;
+  p.a16_out = ln.gamma ? h->y2 : nullptr;
+  p.stats_out = ln.gamma ? h->ln_stats : nullptr;
+  p.ln_stats = ln.s ? h->ln_stats : nullptr;
+  p.ln_nsb = ln.nsb;
+  p.ln_s = ln.s;
   p.M = M;
   p.N = N;
   p.K = K;
@@ -335,6 +384,7 @@ int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], in
   p.scale = 1.0f;
   p.reverse_m = 0;
   const int bn = aihab::gemm_block_n(M, N, h->num_sms);
+  if (n_blocks_out) *n_blocks_out = (N + bn - 1) / bn;
   ProfScope ps(PC_GEMM, 2.0 * M * N * K, s);
   CKL(aihab::launch_gemm(ma, mw[bn == 256 ? 1 : 0], epi == aihab::EPI_BIAS_RES_32 ? &h->m_x : nullptr, p, bn,
                          h->num_sms, s));
@@ -352,13 +402,23 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
     ProfScope ps(PC_LN, 8.0 * M * D, s);
     CKL(aihab::launch_layernorm(h->x, D, h->cls0, L, h->lnpre_g, h->lnpre_b, h->x, nullptr, 0, M, D, s));
   }
-  for (auto& b : h->blocks) {
+  const int layers = static_cast<int>(h->blocks.size());
+  int nsb = 0;  // stat blocks per row written by the last residual GEMM
+  for (int l = 0; l < layers; ++l) {
+    aihab_vit::Block& b = h->blocks[l];
     // x = x + out_proj(attn(in_proj(ln_1(x))))   (clip/model.py:181,184)
-    {
-      ProfScope ps(PC_LN, 6.0 * M * D, s);
-      CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln1_g, b.ln1_b, nullptr, h->y, h->bf16, M, D, s));
+    if (l == 0 || !h->ln_fold) {
+      {
+        ProfScope ps(PC_LN, 6.0 * M * D, s);
+        CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln1_g, b.ln1_b, nullptr, h->y2, h->bf16, M, D, s));
+      }
+      if (run_gemm(h, h->m_y2, b.m_in, M, 3 * D, D, aihab::EPI_BIAS_16, b.b_in, h->big, nullptr, 3 * D, s)) return 1;
+    } else {  // ln_1 folded: y2 = gamma_1 * x and the row statistics came out of the previous c_proj epilogue
+      LnOpt o;
+      o.s = b.s_in;
+      o.nsb = nsb;
+      if (run_gemm(h, h->m_y2, b.m_in, M, 3 * D, D, aihab::EPI_LN_BIAS_16, b.bp_in, h->big, nullptr, 3 * D, s, o)) return 1;
     }
-    if (run_gemm(h, h->m_y, b.m_in, M, 3 * D, D, aihab::EPI_BIAS_16, b.b_in, h->big, nullptr, 3 * D, s)) return 1;
     {
       ProfScope ps(PC_ATTN, 4.0 * n * L * L * D, s);
       if (h->attn_kind == 2)
@@ -368,15 +428,30 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
       else
         CKL(aihab::launch_attention(h->big, h->y, n, L, h->cfg.heads, h->bf16, s));
     }
-    if (run_gemm(h, h->m_y, b.m_out, M, D, D, aihab::EPI_BIAS_RES_32, b.b_out, nullptr, h->x, D, s)) return 1;
-    // x = x + c_proj(quickgelu(c_fc(ln_2(x))))   (clip/model.py:171-175,185)
     {
-      ProfScope ps(PC_LN, 6.0 * M * D, s);
-      CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln2_g, b.ln2_b, nullptr, h->y, h->bf16, M, D, s));
+      LnOpt o;
+      if (h->ln_fold) o.gamma = b.ln2_g;
+      if (run_gemm(h, h->m_y, b.m_out, M, D, D, aihab::EPI_BIAS_RES_32, b.b_out, nullptr, h->x, D, s, o, &nsb)) return 1;
     }
-    if (run_gemm(h, h->m_y, b.m_fc, M, 4 * D, D, aihab::EPI_BIAS_GELU_16, b.b_fc, h->big, nullptr, 4 * D, s))
-      return 1;
-    if (run_gemm(h, h->m_h, b.m_proj, M, D, 4 * D, aihab::EPI_BIAS_RES_32, b.b_proj, nullptr, h->x, D, s)) return 1;
+    // x = x + c_proj(quickgelu(c_fc(ln_2(x))))   (clip/model.py:171-175,185)
+    if (!h->ln_fold) {
+      {
+        ProfScope ps(PC_LN, 6.0 * M * D, s);
+        CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln2_g, b.ln2_b, nullptr, h->y2, h->bf16, M, D, s));
+      }
+      if (run_gemm(h, h->m_y2, b.m_fc, M, 4 * D, D, aihab::EPI_BIAS_GELU_16, b.b_fc, h->big, nullptr, 4 * D, s)) return 1;
+    } else {
+      LnOpt o;
+      o.s = b.s_fc;
+      o.nsb = nsb;
+      if (run_gemm(h, h->m_y2, b.m_fc, M, 4 * D, D, aihab::EPI_LN_BIAS_GELU_16, b.bp_fc, h->big, nullptr, 4 * D, s, o))
+        return 1;
+    }
+    {
+      LnOpt o;
+      if (h->ln_fold && l + 1 < layers) o.gamma = h->blocks[l + 1].ln1_g;  // the last block feeds ln_post (kernel)
+      if (run_gemm(h, h->m_h, b.m_proj, M, D, 4 * D, aihab::EPI_BIAS_RES_32, b.b_proj, nullptr, h->x, D, s, o, &nsb)) return 1;
+    }
   }
   // ln_post on token 0 of every image (clip/model.py:228); rows are L*D apart
   float* o32 = out_dtype == AIHAB_F32 ? static_cast<float*>(feats_out) : nullptr;
@@ -493,6 +568,10 @@ int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, in
     for (int i = 0; i < D; ++i) cls[i] += p0[i];
     if (upload_f32(h, cls.data(), D, &h->cls0)) return bail(1);
   }
+  {
+    const char* e = getenv("AIHAB_LNFOLD");
+    h->ln_fold = !(e && e[0] == '0') && D / 128 <= kMaxStatBlocks;
+  }
   h->blocks.resize(cfg->layers);
   for (int i = 0; i < cfg->layers; ++i) {
     const aihab_vit_block_weights& s = w->blocks[i];
@@ -508,21 +587,28 @@ int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, in
     if (weight_maps(h, b.w_in, 3 * D, D, b.m_in) || weight_maps(h, b.w_out, D, D, b.m_out) ||
         weight_maps(h, b.w_fc, 4 * D, D, b.m_fc) || weight_maps(h, b.w_proj, D, 4 * D, b.m_proj))
       return bail(1);
+    if (h->ln_fold &&
+        (fold_ln(h, s.in_proj_weight, s.in_proj_bias, s.ln_1_weight, s.ln_1_bias, 3 * D, D, &b.s_in, &b.bp_in) ||
+         fold_ln(h, s.c_fc_weight, s.c_fc_bias, s.ln_2_weight, s.ln_2_bias, 4 * D, D, &b.s_fc, &b.bp_fc)))
+      return bail(1);
   }
   // workspace
   const size_t prow = static_cast<size_t>(cfg->max_batch) * h->g2;
   if (dev_alloc(h, &h->patches, prow * h->Kpad * 2) ||
       dev_alloc(h, reinterpret_cast<void**>(&h->x), h->cap_rows * D * 4) || dev_alloc(h, &h->y, h->cap_rows * D * 2) ||
-      dev_alloc(h, &h->big, h->cap_rows * 4 * D * 2))
+      dev_alloc(h, &h->big, h->cap_rows * 4 * D * 2) || dev_alloc(h, &h->y2, h->cap_rows * D * 2) ||
+      dev_alloc(h, reinterpret_cast<void**>(&h->ln_stats), h->cap_rows * kMaxStatBlocks * 2 * sizeof(float)))
     return bail(1);
   if (cudaMemset(h->patches, 0, prow * h->Kpad * 2) != cudaSuccess || cudaMemset(h->y, 0, h->cap_rows * D * 2) != cudaSuccess ||
-      cudaMemset(h->big, 0, h->cap_rows * 4 * D * 2) != cudaSuccess) {
+      cudaMemset(h->big, 0, h->cap_rows * 4 * D * 2) != cudaSuccess ||
+      cudaMemset(h->y2, 0, h->cap_rows * D * 2) != cudaSuccess) {
     fail("aihab_vit_create: cudaMemset failed");
     return bail(1);
   }
   if (aihab::make_tmap_2d_16bit(&h->m_patches, h->patches, prow, h->Kpad, static_cast<uint64_t>(h->Kpad) * 2, 128, h->bf16) != cudaSuccess ||
       aihab::make_tmap_2d_16bit(&h->m_y, h->y, h->cap_rows, D, static_cast<uint64_t>(D) * 2, 128, h->bf16) != cudaSuccess ||
       aihab::make_tmap_2d_16bit(&h->m_h, h->big, h->cap_rows, 4 * D, static_cast<uint64_t>(4 * D) * 2, 128, h->bf16) != cudaSuccess ||
+      aihab::make_tmap_2d_16bit(&h->m_y2, h->y2, h->cap_rows, D, static_cast<uint64_t>(D) * 2, 128, h->bf16) != cudaSuccess ||
       aihab::make_tmap_2d_f32_box32(&h->m_x, h->x, h->cap_rows, D, static_cast<uint64_t>(D) * 4) != cudaSuccess) {
     fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the workspace");
     return bail(1);

@@ -27,7 +27,7 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kRes ? 4 * RS * RES_BOX : 4 * 32 * 128;  // per epilogue warp
-  static constexpr int kBiasBytes = 2 * BN * 4;
+  static constexpr int kBiasBytes = 4 * BN * 4;  // [2][BN] bias + [2][BN] auxiliary per-column vector (s_n / gamma)
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kStages * kABytes;
   static constexpr int kOffStaging = kStages * kStageBytes;
@@ -51,7 +51,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   using L = SmemLayout<BN, EPI>;
   constexpr int kStages = L::kStages;
-  constexpr bool kOut16 = (EPI == EPI_BIAS_16 || EPI == EPI_BIAS_GELU_16);
+  constexpr bool kLn = (EPI == EPI_LN_BIAS_16 || EPI == EPI_LN_BIAS_GELU_16);
+  constexpr bool kGelu = (EPI == EPI_BIAS_GELU_16 || EPI == EPI_LN_BIAS_GELU_16);
+  constexpr bool kOut16 = (EPI == EPI_BIAS_16 || EPI == EPI_BIAS_GELU_16 || kLn);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -192,12 +194,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t aphase = (it >> 1) & 1;
 
       float* sb = sBias + as * BN;
+      float* sx = sBias + (2 + as) * BN;  // s_n (LayerNorm consumer) or gamma (LayerNorm producer)
+      const bool ln_prod = (EPI == EPI_BIAS_RES_32) && p.ln_gamma != nullptr;
       if constexpr (EPI != EPI_PATCH_32) {
+        const float* aux = kLn ? p.ln_s : p.ln_gamma;
         for (int i = et; i < BN; i += 128) {
           const int n = n0 + i;
           sb[i] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+          if (kLn || ln_prod) sx[i] = n < p.N ? __ldg(aux + n) : 0.0f;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      // LayerNorm consumer: statistics of this thread's row from the producer's per-tile partial sums
+      float ln_r = 1.0f, ln_nrm = 0.0f;
+      if constexpr (kLn) {
+        const int grow = m0 + lane;
+        if (grow < p.M) {
+          const float* st = p.ln_stats + static_cast<size_t>(grow) * p.ln_nsb * 2;
+          float s1 = 0.f, s2 = 0.f;
+          for (int b = 0; b < p.ln_nsb; ++b) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(st) + b);
+            s1 += v.x;
+            s2 += v.y;
+          }
+          const float inv_k = 1.0f / static_cast<float>(p.K);
+          const float mu = s1 * inv_k;
+          const float var = fmaxf(fmaf(-mu, mu, s2 * inv_k), 0.0f);
+          ln_r = rsqrtf(var + 1e-5f);
+          ln_nrm = -ln_r * mu;
+        }
       }
 
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
@@ -214,11 +239,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           uint32_t pk[32];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float a0 = __uint_as_float(r0[2 * j]) + sb[c * 64 + 2 * j];
-            float a1 = __uint_as_float(r0[2 * j + 1]) + sb[c * 64 + 2 * j + 1];
-            float b0 = __uint_as_float(r1[2 * j]) + sb[c * 64 + 32 + 2 * j];
-            float b1 = __uint_as_float(r1[2 * j + 1]) + sb[c * 64 + 32 + 2 * j + 1];
-            if constexpr (EPI == EPI_BIAS_GELU_16) {
+            float a0, a1, b0, b1;
+            if constexpr (kLn) {
+              a0 = fmaf(ln_r, __uint_as_float(r0[2 * j]), fmaf(ln_nrm, sx[c * 64 + 2 * j], sb[c * 64 + 2 * j]));
+              a1 = fmaf(ln_r, __uint_as_float(r0[2 * j + 1]), fmaf(ln_nrm, sx[c * 64 + 2 * j + 1], sb[c * 64 + 2 * j + 1]));
+              b0 = fmaf(ln_r, __uint_as_float(r1[2 * j]), fmaf(ln_nrm, sx[c * 64 + 32 + 2 * j], sb[c * 64 + 32 + 2 * j]));
+              b1 = fmaf(ln_r, __uint_as_float(r1[2 * j + 1]),
+                        fmaf(ln_nrm, sx[c * 64 + 32 + 2 * j + 1], sb[c * 64 + 32 + 2 * j + 1]));
+            } else {
+              a0 = __uint_as_float(r0[2 * j]) + sb[c * 64 + 2 * j];
+              a1 = __uint_as_float(r0[2 * j + 1]) + sb[c * 64 + 2 * j + 1];
+              b0 = __uint_as_float(r1[2 * j]) + sb[c * 64 + 32 + 2 * j];
+              b1 = __uint_as_float(r1[2 * j + 1]) + sb[c * 64 + 32 + 2 * j + 1];
+            }
+            if constexpr (kGelu) {
               a0 = quick_gelu(a0);
               a1 = quick_gelu(a1);
               b0 = quick_gelu(b0);
@@ -248,6 +282,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           __syncwarp();
         }
       } else if constexpr (EPI == EPI_BIAS_RES_32) {
+        float ln_s1 = 0.f, ln_s2 = 0.f;  // LayerNorm producer: this row's sum / sum of squares over the tile
+        const int prow = m0 + lane;
 #pragma unroll 1
         for (int c = 0; c < CPT; ++c, ++q) {
           const int slot = q % RS;
@@ -265,6 +301,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             v.z += __uint_as_float(r[4 * u + 2]) + sb[c * 32 + 4 * u + 2];
             v.w += __uint_as_float(r[4 * u + 3]) + sb[c * 32 + 4 * u + 3];
             *px = v;
+            if (ln_prod) {  // reuse r[] for the packed gamma * x_new row segment
+              ln_s1 += (v.x + v.y) + (v.z + v.w);
+              ln_s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ln_s2))));
+              const float g0 = sx[c * 32 + 4 * u], g1 = sx[c * 32 + 4 * u + 1], g2 = sx[c * 32 + 4 * u + 2],
+                          g3 = sx[c * 32 + 4 * u + 3];
+              r[2 * u] = bf16 ? ptx::pack2<true>(g0 * v.x, g1 * v.y) : ptx::pack2<false>(g0 * v.x, g1 * v.y);
+              r[2 * u + 1] = bf16 ? ptx::pack2<true>(g2 * v.z, g3 * v.w) : ptx::pack2<false>(g2 * v.z, g3 * v.w);
+            }
+          }
+          if (ln_prod && prow < p.M && n0 + c * 32 < p.N) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.a16_out) +
+                                                  static_cast<size_t>(prow) * p.N + n0 + c * 32);
+            dst[0] = make_uint4(r[0], r[1], r[2], r[3]);
+            dst[1] = make_uint4(r[4], r[5], r[6], r[7]);
+            dst[2] = make_uint4(r[8], r[9], r[10], r[11]);
+            dst[3] = make_uint4(r[12], r[13], r[14], r[15]);
           }
           ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
           __syncwarp();
@@ -275,6 +327,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             res_prefetch(q + RS - 1);   // ... which is exactly the slot box q+RS-1 lands in
           }
           __syncwarp();
+        }
+        if (ln_prod && prow < p.M) {
+          *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(prow) * n_blocks + n_blk) * 2) =
+              make_float2(ln_s1, ln_s2);
         }
       } else {
 #pragma unroll 1
@@ -379,6 +435,8 @@ cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, const CUtens
     case EPI_BIAS_RES_32: return launch_one<BN, EPI_BIAS_RES_32>(ta, tw, tc, p, grid, stream);
     case EPI_PATCH_32: return launch_one<BN, EPI_PATCH_32>(ta, tw, tc, p, grid, stream);
     case EPI_SCALE_32: return launch_one<BN, EPI_SCALE_32>(ta, tw, tc, p, grid, stream);
+    case EPI_LN_BIAS_16: return launch_one<BN, EPI_LN_BIAS_16>(ta, tw, tc, p, grid, stream);
+    case EPI_LN_BIAS_GELU_16: return launch_one<BN, EPI_LN_BIAS_GELU_16>(ta, tw, tc, p, grid, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -398,7 +456,8 @@ cudaError_t gemm_init() {
 #define AIHAB_SET(BN, EPI) \
   if ((e = set_attr<BN, EPI>()) != cudaSuccess) return e;
   AIHAB_SET(256, EPI_BIAS_16) AIHAB_SET(256, EPI_BIAS_GELU_16) AIHAB_SET(256, EPI_BIAS_RES_32)
-  AIHAB_SET(256, EPI_PATCH_32) AIHAB_SET(256, EPI_SCALE_32)
+  AIHAB_SET(256, EPI_PATCH_32) AIHAB_SET(256, EPI_SCALE_32) AIHAB_SET(256, EPI_LN_BIAS_16)
+  AIHAB_SET(256, EPI_LN_BIAS_GELU_16) AIHAB_SET(128, EPI_LN_BIAS_16) AIHAB_SET(128, EPI_LN_BIAS_GELU_16)
   AIHAB_SET(128, EPI_BIAS_16) AIHAB_SET(128, EPI_BIAS_GELU_16) AIHAB_SET(128, EPI_BIAS_RES_32)
   AIHAB_SET(128, EPI_PATCH_32) AIHAB_SET(128, EPI_SCALE_32)
 #undef AIHAB_SET
@@ -454,7 +513,11 @@ cudaError_t make_tmap_2d_f32_box32(CUtensorMap* map, const void* base, uint64_t 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, const CUtensorMap* tmap_c,
                         const GemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorInvalidValue;
-  const bool out16 = (p.epilogue == EPI_BIAS_16 || p.epilogue == EPI_BIAS_GELU_16);
+  const bool ln = (p.epilogue == EPI_LN_BIAS_16 || p.epilogue == EPI_LN_BIAS_GELU_16);
+  const bool out16 = (p.epilogue == EPI_BIAS_16 || p.epilogue == EPI_BIAS_GELU_16 || ln);
+  if (ln && (p.ln_stats == nullptr || p.ln_s == nullptr || p.ln_nsb <= 0 || p.bias == nullptr)) return cudaErrorInvalidValue;
+  if (p.epilogue == EPI_BIAS_RES_32 && p.ln_gamma != nullptr && (p.a16_out == nullptr || p.stats_out == nullptr))
+    return cudaErrorInvalidValue;
   if (out16 && ((p.N & 7) || (p.ldo & 7) || p.out16 == nullptr)) return cudaErrorInvalidValue;
   if (!out16 && ((p.N & 3) || (p.ldo & 3) || p.out32 == nullptr)) return cudaErrorInvalidValue;
   if (p.epilogue == EPI_PATCH_32 && (p.pos == nullptr || p.g2 <= 0)) return cudaErrorInvalidValue;

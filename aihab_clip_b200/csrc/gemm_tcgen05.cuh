@@ -24,6 +24,11 @@ enum GemmEpilogue : int {
   EPI_BIAS_RES_32 = 2,   // out32[m,n] += acc + bias[n]   (fp32 residual stream) clip/model.py:184-185
   EPI_PATCH_32 = 3,      // out32[tok(m),n] = acc + pos[1 + m % g2, n]         clip/model.py:217-221
   EPI_SCALE_32 = 4,      // out32[m,n] = scale * acc (+ bias[n] if bias)       plain fp32 store
+  // LayerNorm folded into the consumer GEMM: A holds gamma * x (16-bit, un-normalised), the epilogue applies
+  //   out = r_m * acc - r_m * mu_m * s_n + b'_n,  s_n = sum_k gamma_k W_nk,  b'_n = bias_n + sum_k beta_k W_nk,
+  // with the row statistics (mu, r = rsqrt(var + 1e-5)) rebuilt from the partial sums the producer GEMM stored.
+  EPI_LN_BIAS_16 = 5,       // ln_1 -> in_proj                                  clip/model.py:181,184
+  EPI_LN_BIAS_GELU_16 = 6,  // ln_2 -> c_fc -> QuickGELU                        clip/model.py:172,185
 };
 
 struct GemmParams {
@@ -38,6 +43,16 @@ struct GemmParams {
   int g2;             // EPI_PATCH_32: patches per image (L = g2 + 1)
   float scale;        // EPI_SCALE_32
   int reverse_m;      // walk M blocks from last to first (L2 reuse of the producer's freshest rows)
+  // EPI_BIAS_RES_32 as LayerNorm PRODUCER (optional, ln_gamma != nullptr): besides updating the residual it stores
+  //   a16_out[m,n] = round16(ln_gamma[n] * x_new[m,n])            (A operand of the next GEMM, ld = N)
+  //   stats_out[m, n_blk, 0..1] = (sum, sum of squares) of x_new over this tile's columns (deterministic order)
+  const float* ln_gamma;
+  void* a16_out;
+  float* stats_out;
+  // EPI_LN_* as LayerNorm CONSUMER: partial sums written by the producer ([M, ln_nsb, 2]) and s_n ([N]); `bias` = b'
+  const float* ln_stats;
+  int ln_nsb;
+  const float* ln_s;
 };
 
 // Encodes a 2-D tiled tensor map over a row-major [rows, cols] 16-bit matrix with a {64, box_rows} box and
