@@ -11,8 +11,14 @@ namespace {
 constexpr int BM = 128;      // UMMA M (one CTA, cta_group::1): accumulator row i <-> TMEM lane i
 constexpr int BK = 64;       // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;   // fixed for 16-bit operands
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_WARP0 = 4;  // warps 4..7 are the epilogue (warp % 4 selects the TMEM lane quadrant)
+constexpr int EPI_WARP0 = 4;  // warps 4.. are the epilogue (warp % 4 selects the TMEM lane quadrant)
+__host__ __device__ constexpr bool epi_out16(int epi) {
+  return epi == EPI_BIAS_16 || epi == EPI_BIAS_GELU_16 || epi == EPI_LN_BIAS_16 || epi == EPI_LN_BIAS_GELU_16;
+}
+// 16-bit-output epilogues do the activation math (bias / LayerNorm fold / QuickGELU): two warps per TMEM lane quadrant
+// (8 epilogue warps, 384 threads) so they keep up with the MMA; the fp32 epilogues are memory-bound: one warp each.
+__host__ __device__ constexpr int epi_warps(int epi) { return epi_out16(epi) ? 8 : 4; }
+__host__ __device__ constexpr int num_threads(int epi) { return (EPI_WARP0 + epi_warps(epi)) * 32; }
 
 constexpr int RS = 4;           // residual ring slots per epilogue warp (EPI_BIAS_RES_32)
 constexpr int RES_BOX = 32 * 128;  // 32 rows x 32 fp32 = 4 KB TMA box, SWIZZLE_128B
@@ -26,7 +32,8 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kRes ? 4 * RS * RES_BOX : 4 * 32 * 128;  // per epilogue warp
+  // residual ring (4 warps x RS boxes) + 4 x 2 KB for the coalesced gamma*x store | 8 or 4 warps x staging tile
+  static constexpr int kStagingBytes = kRes ? 4 * RS * RES_BOX + 4 * 2048 : (epi_out16(EPI) ? 8 * 2048 : 4 * 4096);
   static constexpr int kBiasBytes = 4 * BN * 4;  // [2][BN] bias + [2][BN] auxiliary per-column vector (s_n / gamma)
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kStages * kABytes;
@@ -46,7 +53,7 @@ __device__ __forceinline__ float quick_gelu(float x) {
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   using L = SmemLayout<BN, EPI>;
@@ -87,7 +94,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
-      ptx::mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty_bar[i], epi_warps(EPI));  // one arrive per epilogue warp
     }
     for (int i = 0; i < 4 * RS; ++i) ptx::mbar_init(&res_full_bar[i], 1);
     ptx::fence_mbar_init();
@@ -157,9 +164,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------ epilogue
-    const int ew = warp - EPI_WARP0;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    uint8_t* stg = sStaging + ew * (32 * 128);
-    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
+    constexpr int kEpiThreads = epi_warps(EPI) * 32;
+    const int ew = warp & 3;                   // TMEM lanes [32*ew, 32*ew+32) (hardware: warp % 4)
+    const int ehalf = (warp - EPI_WARP0) >> 2;  // 0, or 0/1 when two warps share a quadrant
+    uint8_t* stg = sStaging + (kOut16 ? (warp - EPI_WARP0) * 2048 : ew * 4096);
+    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..kEpiThreads-1
     const bool bf16 = p.ab_format != 0;
     // EPI_BIAS_RES_32: every warp streams its 32-row slice of the fp32 residual through a private ring of 4 KB
     // TMA boxes (load -> add in place -> TMA store), prefetching RS-1 boxes ahead across tile boundaries.
@@ -198,12 +207,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const bool ln_prod = (EPI == EPI_BIAS_RES_32) && p.ln_gamma != nullptr;
       if constexpr (EPI != EPI_PATCH_32) {
         const float* aux = kLn ? p.ln_s : p.ln_gamma;
-        for (int i = et; i < BN; i += 128) {
+        for (int i = et; i < BN; i += kEpiThreads) {
           const int n = n0 + i;
           sb[i] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.0f;
           if (kLn || ln_prod) sx[i] = n < p.N ? __ldg(aux + n) : 0.0f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
       // LayerNorm consumer: statistics of this thread's row from the producer's per-tile partial sums
       float ln_r = 1.0f, ln_nrm = 0.0f;
@@ -230,49 +239,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
 
       if constexpr (kOut16) {
+        // 32-column chunks, dealt alternately to the two warps of a lane quadrant
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          uint32_t r0[32], r1[32];
-          ptx::tmem_ld_32x32(taddr + c * 64, r0);
-          ptx::tmem_ld_32x32(taddr + c * 64 + 32, r1);
+        for (int c = ehalf; c < BN / 32; c += 2) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, r);
           ptx::tmem_ld_wait();
-          uint32_t pk[32];
+          uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float a0, a1, b0, b1;
+            float a0, a1;
             if constexpr (kLn) {
-              a0 = fmaf(ln_r, __uint_as_float(r0[2 * j]), fmaf(ln_nrm, sx[c * 64 + 2 * j], sb[c * 64 + 2 * j]));
-              a1 = fmaf(ln_r, __uint_as_float(r0[2 * j + 1]), fmaf(ln_nrm, sx[c * 64 + 2 * j + 1], sb[c * 64 + 2 * j + 1]));
-              b0 = fmaf(ln_r, __uint_as_float(r1[2 * j]), fmaf(ln_nrm, sx[c * 64 + 32 + 2 * j], sb[c * 64 + 32 + 2 * j]));
-              b1 = fmaf(ln_r, __uint_as_float(r1[2 * j + 1]),
-                        fmaf(ln_nrm, sx[c * 64 + 32 + 2 * j + 1], sb[c * 64 + 32 + 2 * j + 1]));
+              a0 = fmaf(ln_r, __uint_as_float(r[2 * j]), fmaf(ln_nrm, sx[c * 32 + 2 * j], sb[c * 32 + 2 * j]));
+              a1 = fmaf(ln_r, __uint_as_float(r[2 * j + 1]), fmaf(ln_nrm, sx[c * 32 + 2 * j + 1], sb[c * 32 + 2 * j + 1]));
             } else {
-              a0 = __uint_as_float(r0[2 * j]) + sb[c * 64 + 2 * j];
-              a1 = __uint_as_float(r0[2 * j + 1]) + sb[c * 64 + 2 * j + 1];
-              b0 = __uint_as_float(r1[2 * j]) + sb[c * 64 + 32 + 2 * j];
-              b1 = __uint_as_float(r1[2 * j + 1]) + sb[c * 64 + 32 + 2 * j + 1];
+              a0 = __uint_as_float(r[2 * j]) + sb[c * 32 + 2 * j];
+              a1 = __uint_as_float(r[2 * j + 1]) + sb[c * 32 + 2 * j + 1];
             }
             if constexpr (kGelu) {
               a0 = quick_gelu(a0);
               a1 = quick_gelu(a1);
-              b0 = quick_gelu(b0);
-              b1 = quick_gelu(b1);
             }
             pk[j] = bf16 ? ptx::pack2<true>(a0, a1) : ptx::pack2<false>(a0, a1);
-            pk[16 + j] = bf16 ? ptx::pack2<true>(b0, b1) : ptx::pack2<false>(b0, b1);
           }
+          // transpose through a 32 x 64 B staging tile (16 B units XOR-swizzled by (row >> 1) & 3: conflict-free both
+          // ways) so that every global store instruction writes 8 complete 64 B row segments
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) =
+          for (int u = 0; u < 4; ++u) {
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) =
                 make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
           }
           __syncwarp();
-          const int u = lane & 7;
-          const int gcol = n0 + c * 64 + u * 8;
+          const int u = lane & 3;
+          const int gcol = n0 + c * 32 + u * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = i * 4 + (lane >> 3);
-            const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((u ^ (row & 7)) << 4));
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + (lane >> 2);
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 64 + ((u ^ ((row >> 1) & 3)) << 4));
             const int grow = m0 + row;
             if (grow < p.M && gcol < p.N) {
               *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + static_cast<size_t>(grow) * p.ldo +
@@ -310,13 +313,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               r[2 * u + 1] = bf16 ? ptx::pack2<true>(g2 * v.z, g3 * v.w) : ptx::pack2<false>(g2 * v.z, g3 * v.w);
             }
           }
-          if (ln_prod && prow < p.M && n0 + c * 32 < p.N) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.a16_out) +
-                                                  static_cast<size_t>(prow) * p.N + n0 + c * 32);
-            dst[0] = make_uint4(r[0], r[1], r[2], r[3]);
-            dst[1] = make_uint4(r[4], r[5], r[6], r[7]);
-            dst[2] = make_uint4(r[8], r[9], r[10], r[11]);
-            dst[3] = make_uint4(r[12], r[13], r[14], r[15]);
+          if (ln_prod) {  // gamma * x_new: transpose through smem so each store covers 8 complete 64 B row segments
+            uint8_t* ast = sStaging + 4 * RS * RES_BOX + ew * 2048;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              *reinterpret_cast<uint4*>(ast + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+            }
+            __syncwarp();
+            const int u = lane & 3;
+            const int gcol = n0 + c * 32 + u * 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = i * 8 + (lane >> 2);
+              const uint4 v = *reinterpret_cast<const uint4*>(ast + row * 64 + ((u ^ ((row >> 1) & 3)) << 4));
+              if (m0 + row < p.M && gcol < p.N)
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.a16_out) +
+                                          static_cast<size_t>(m0 + row) * p.N + gcol) = v;
+            }
           }
           ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
           __syncwarp();
@@ -422,7 +436,7 @@ cudaError_t set_attr() {
 template <int BN, int EPI>
 cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const GemmParams& p,
                        int grid, cudaStream_t stream) {
-  gemm_kernel<BN, EPI><<<grid, NUM_THREADS, SmemLayout<BN, EPI>::kDynamic, stream>>>(ta, tw, tc, p);
+  gemm_kernel<BN, EPI><<<grid, num_threads(EPI), SmemLayout<BN, EPI>::kDynamic, stream>>>(ta, tw, tc, p);
   return cudaGetLastError();
 }
 
