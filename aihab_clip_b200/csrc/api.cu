@@ -772,6 +772,7 @@ int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype
   p.pos = pos;
   p.g2 = g2;
   p.scale = scale;
+  if (const char* dbg = getenv("AIHAB_GEMM_DEBUG")) p.reverse_m = atoi(dbg);  // 77 no epilogue, 78 TMEM loads only, 79 no stores
   CUtensorMap mc;
   const bool res = epilogue == AIHAB_EPI_BIAS_RES_32;
   if (res) {

@@ -1,0 +1,80 @@
+"""Throughput of the other BASELINE.json configs on one B200 (device-resident uint8 inputs, CUDA events).
+    python tools/bench_configs.py [--quick]
+Not the judged benchmark (bench.py is); these are the parity-test configurations measured for the record."""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from aihab_clip_b200 import _lib, ops  # noqa: E402
+from aihab_clip_b200.clip.model import build_model  # noqa: E402
+from aihab_clip_b200.extraction import ZeroShotHead, encode_and_score  # noqa: E402
+from aihab_clip_b200.weights import GEOMETRIES, make_state_dict  # noqa: E402
+from bench import flops_per_image, measured_peaks  # noqa: E402
+
+
+def time_steps(fn, steps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--dtype", default="fp16")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    peaks = measured_peaks()
+    rows = []
+    cases = [("ViT-B/32", 512, 20), ("ViT-B/16", 128, 20), ("ViT-L/14", 128, 20), ("ViT-L/14@336px", 64, 20)]
+    for arch, batch, classes in cases:
+        geom = GEOMETRIES[arch]
+        model = build_model(make_state_dict(geom, 0, with_text=False if False else True)).to(dev).float()
+        model.visual.compute_dtype = args.dtype
+        model.visual.max_batch = batch
+        tw = torch.nn.functional.normalize(torch.randn(classes, geom.embed_dim, device=dev), dim=1).t().contiguous()
+        head = ZeroShotHead.from_model(model, tw, dev)
+        R = geom.image_resolution
+        imgs = [torch.randint(0, 256, (batch, R, R, 3), dtype=torch.uint8, device=dev) for _ in range(3)]
+        i = [0]
+
+        def step():
+            encode_and_score(model, imgs[i[0] % 3], head, 1)
+            i[0] += 1
+
+        ms = time_steps(step, 3 if args.quick else 10)
+        ips = batch / ms * 1e3
+        tf = ips * flops_per_image(geom, classes) / 1e12
+        rows.append({"config": f"{arch} encode_image + logits, batch {batch}, {R}px", "ms_per_step": round(ms, 3),
+                     "images_per_s": round(ips, 1), "tflops": round(tf, 1),
+                     "frac_of_tensor_peak": round(tf / peaks["tensor"], 3)})
+        del model, head, imgs
+        torch.cuda.empty_cache()
+    # config 5: scoring over cached features
+    n = 200_000 if args.quick else 1_000_000
+    feats = torch.randn(n, 768, device=dev)
+    proj = torch.randn(768, 512, device=dev) * 768 ** -0.5
+    tw = torch.nn.functional.normalize(torch.randn(1000, 512, device=dev), dim=1).t().contiguous()
+    ms = time_steps(lambda: ops.score(feats, proj, tw, 100.0, 5, want_emb=False, want_logits=False), 2, warm=1)
+    rows.append({"config": f"scoring {n} x 768 -> proj 512 -> 1000 classes -> top-5 (fp32 CUDA cores)",
+                 "ms_per_step": round(ms, 2), "rows_per_s": round(n / ms * 1e3), "tflops": round(2.0 * n * (768 * 512 + 512 * 1000) / ms / 1e9, 2)})
+    for r in rows:
+        print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()
