@@ -119,6 +119,22 @@ int device_of(const void* p) {
   return d;
 }
 
+// Stream-ordered temporaries (aihab_score / aihab_score16) come from the device's default memory pool; keep freed
+// blocks cached in the pool instead of returning them to the driver at every synchronisation point.
+void keep_pool_warm(int dev) {
+  static std::mutex mu;
+  static std::map<int, bool> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t threshold = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  cudaGetLastError();
+  done[dev] = true;
+}
+
 int sm_count(int dev) {
   static std::mutex mu;
   static std::map<int, int> cache;
@@ -717,6 +733,7 @@ int aihab_score(const float* feats, int n, int D, const float* proj, int E, cons
     return 0;
   }
   // rows per pass bounded so temporaries stay small (config 5: 1M rows x 1000 classes)
+  keep_pool_warm(dev);
   const int chunk = 65536;
   float *emb_tmp = nullptr, *logit_tmp = nullptr;
   const int rows_tmp = std::min(n, chunk);
@@ -742,6 +759,78 @@ int aihab_score(const float* feats, int n, int D, const float* proj, int E, cons
     }
   }
   if (emb_tmp) CK(cudaFreeAsync(emb_tmp, s));
+  if (logit_tmp) CK(cudaFreeAsync(logit_tmp, s));
+  return 0;
+}
+
+int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj16, int E, const float* text_w, int C,
+                  float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx, float* topk_val,
+                  void* stream) {
+  if (n < 0 || D <= 0 || E <= 0 || C <= 0) return fail("aihab_score16: bad argument");
+  if (n == 0) return 0;
+  if (feats16 == nullptr || proj16 == nullptr || text_w == nullptr) return fail("aihab_score16: null buffer");
+  if (dtype != AIHAB_F16 && dtype != AIHAB_BF16) return fail("aihab_score16: dtype must be AIHAB_F16 or AIHAB_BF16");
+  if ((D & 7) || (E & 7) || (C & 3)) return fail("aihab_score16: needs D % 8 == 0, E % 8 == 0, C % 4 == 0");
+  if (k < 0 || k > 16 || k > C || (k > 0 && topk_idx == nullptr)) return fail("aihab_score16: bad k (0..16, <= C)");
+  const int dev = device_of(feats16);
+  DeviceGuard guard(dev);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(aihab::gemm_init());
+  keep_pool_warm(dev);
+  const int bf16 = dtype == AIHAB_BF16;
+  const int sms = sm_count(dev);
+  const int chunk = 32768;
+  const int rows_tmp = std::min(n, chunk);
+  void *projT = nullptr, *w3 = nullptr, *a3 = nullptr;
+  float *emb_raw = nullptr, *logit_tmp = nullptr;
+  CK(cudaMallocAsync(&projT, static_cast<size_t>(E) * D * 2, s));
+  CK(cudaMallocAsync(&w3, static_cast<size_t>(C) * 3 * E * 2, s));
+  CK(cudaMallocAsync(&a3, static_cast<size_t>(rows_tmp) * 3 * E * 2, s));
+  CK(cudaMallocAsync(&emb_raw, static_cast<size_t>(rows_tmp) * E * 4, s));
+  if (logits_out == nullptr) CK(cudaMallocAsync(&logit_tmp, static_cast<size_t>(rows_tmp) * C * 4, s));
+  ProfScope ps(PC_SCORE, 2.0 * n * (static_cast<double>(D) * E + static_cast<double>(E) * C), s);
+  CKL(aihab::launch_transpose16(proj16, projT, D, E, s));   // [D, E] -> [E, D]: K-major operand B
+  CKL(aihab::launch_split_textw(text_w, E, C, w3, s));      // [E, C] fp32 -> [C, 3E] fp16 (hi | lo | hi)
+  for (int i0 = 0; i0 < n; i0 += chunk) {
+    const int nb = std::min(chunk, n - i0);
+    const uint8_t* f = static_cast<const uint8_t*>(feats16) + static_cast<size_t>(i0) * D * 2;
+    aihab::GemmParams p{};
+    CUtensorMap ma, mw;
+    // emb_raw = feats16 @ proj16: products of 16-bit values are exact in fp32, so only the summation order differs
+    // from the fp32 reference (methods/ProLIP.py:40)
+    int bn = aihab::gemm_block_n(nb, E, sms);
+    CK(aihab::make_tmap_2d_16bit(&ma, f, nb, D, static_cast<uint64_t>(D) * 2, 128, bf16));
+    CK(aihab::make_tmap_2d_16bit(&mw, projT, E, D, static_cast<uint64_t>(D) * 2, bn, bf16));
+    p.M = nb;
+    p.N = E;
+    p.K = D;
+    p.ab_format = bf16;
+    p.epilogue = aihab::EPI_SCALE_32;
+    p.out32 = emb_raw;
+    p.ldo = E;
+    p.scale = 1.0f;
+    CKL(aihab::launch_gemm(ma, mw, nullptr, p, bn, sms, s));
+    CKL(aihab::launch_l2norm_split(emb_raw, emb_out ? emb_out + static_cast<size_t>(i0) * E : nullptr, a3, nb, E, s));
+    // logits = scale * (e_hi w_hi + e_hi w_lo + e_lo w_hi): one K = 3E fp16 GEMM (methods/utils.py:185)
+    float* lg = logits_out ? logits_out + static_cast<size_t>(i0) * C : logit_tmp;
+    bn = aihab::gemm_block_n(nb, C, sms);
+    CK(aihab::make_tmap_2d_16bit(&ma, a3, nb, 3 * E, static_cast<uint64_t>(3 * E) * 2, 128, 0));
+    CK(aihab::make_tmap_2d_16bit(&mw, w3, C, 3 * E, static_cast<uint64_t>(3 * E) * 2, bn, 0));
+    p.N = C;
+    p.K = 3 * E;
+    p.ab_format = 0;
+    p.out32 = lg;
+    p.ldo = C;
+    p.scale = scale;
+    CKL(aihab::launch_gemm(ma, mw, nullptr, p, bn, sms, s));
+    if (k > 0)
+      CKL(aihab::launch_topk(lg, nb, C, k, topk_idx + static_cast<size_t>(i0) * k,
+                             topk_val ? topk_val + static_cast<size_t>(i0) * k : nullptr, s));
+  }
+  CK(cudaFreeAsync(projT, s));
+  CK(cudaFreeAsync(w3, s));
+  CK(cudaFreeAsync(a3, s));
+  CK(cudaFreeAsync(emb_raw, s));
   if (logit_tmp) CK(cudaFreeAsync(logit_tmp, s));
   return 0;
 }

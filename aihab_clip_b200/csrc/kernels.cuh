@@ -64,6 +64,12 @@ cudaError_t launch_score_fused(const float* feats, int n, int D, const float* pr
                                float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx,
                                float* topk_val, cudaStream_t stream);
 
+// tensor-core scoring helpers (aihab_score16): 16-bit transpose, fp16 hi/lo splits of the text weights and of the
+// normalised embedding (A' = e_hi | e_hi | e_lo against W' = w_hi | w_lo | w_hi reproduces the fp32 product to ~2^-21)
+cudaError_t launch_transpose16(const void* src, void* dst, int R, int Cc, cudaStream_t stream);
+cudaError_t launch_split_textw(const float* w, int E, int C, void* out, cudaStream_t stream);
+cudaError_t launch_l2norm_split(const float* emb, float* emb_out, void* a3, int rows, int E, cudaStream_t stream);
+
 // ---- preprocessing (data/clip_transforms.py:50-56; Pillow ImagingResample fixed-point bicubic)
 struct ResampleTables {
   // device pointers; *_bounds = {first input index, tap count} per output index; coeffs [out, ksize] int32 (2^22)

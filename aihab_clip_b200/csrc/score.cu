@@ -4,6 +4,7 @@
 // (topk, sorted, lowest index first among exact ties).
 #include "kernels.cuh"
 
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace aihab {
@@ -269,7 +270,88 @@ __global__ void __launch_bounds__(256) score_fused_kernel(const float* __restric
   }
 }
 
+// ---- tensor-core scoring helpers (aihab_score16) -------------------------------------------------------------
+// 16-bit transpose: src [R, Cc] -> dst [Cc, R]   (visual.proj [D, E] -> [E, D], the K-major UMMA operand B)
+__global__ void transpose16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int R, int Cc) {
+  __shared__ uint16_t t[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < R && c < Cc) ? src[static_cast<size_t>(r) * Cc + c] : 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < Cc && r < R) dst[static_cast<size_t>(c) * R + r] = t[threadIdx.x][i];
+  }
+}
+
+__device__ __forceinline__ void split_hi_lo(float v, uint16_t& hi, uint16_t& lo) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  hi = *reinterpret_cast<const uint16_t*>(&h);
+  lo = *reinterpret_cast<const uint16_t*>(&l);
+}
+
+// text weights fp32 [E, C] -> [C, 3E] fp16 rows (w_hi | w_lo | w_hi): the B operand matching A' = (e_hi | e_hi | e_lo)
+__global__ void split_textw_kernel(const float* __restrict__ w, int E, int C, uint16_t* __restrict__ out) {
+  const long total = static_cast<long>(E) * C;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<long>(e) * C);
+    uint16_t hi, lo;
+    split_hi_lo(w[i], hi, lo);
+    uint16_t* row = out + static_cast<size_t>(c) * 3 * E;
+    row[e] = hi;
+    row[E + e] = lo;
+    row[2 * E + e] = hi;
+  }
+}
+
+// rows of emb fp32 [rows, E]: L2-normalise (F.normalize eps) -> optional fp32 copy + A' [rows, 3E] fp16 (hi | hi | lo)
+__global__ void __launch_bounds__(128) l2norm_split_kernel(const float* __restrict__ emb, float* __restrict__ emb_out,
+                                                           uint16_t* __restrict__ a3, int rows, int E) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* src = emb + static_cast<size_t>(row) * E;
+  float s = 0.f;
+  for (int c = lane; c < E; c += 32) s = fmaf(src[c], src[c], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float denom = fmaxf(sqrtf(s), 1e-12f);
+  uint16_t* dst = a3 + static_cast<size_t>(row) * 3 * E;
+  for (int c = lane; c < E; c += 32) {
+    const float v = src[c] / denom;
+    if (emb_out != nullptr) emb_out[static_cast<size_t>(row) * E + c] = v;
+    uint16_t hi, lo;
+    split_hi_lo(v, hi, lo);
+    dst[c] = hi;
+    dst[E + c] = hi;
+    dst[2 * E + c] = lo;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_transpose16(const void* src, void* dst, int R, int Cc, cudaStream_t stream) {
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32), block(32, 8);
+  transpose16_kernel<<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), R, Cc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_textw(const float* w, int E, int C, void* out, cudaStream_t stream) {
+  const long total = static_cast<long>(E) * C;
+  const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 8));
+  split_textw_kernel<<<grid, 256, 0, stream>>>(w, E, C, static_cast<uint16_t*>(out));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_l2norm_split(const float* emb, float* emb_out, void* a3, int rows, int E, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  l2norm_split_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(emb, emb_out, static_cast<uint16_t*>(a3), rows, E);
+  return cudaGetLastError();
+}
 
 bool score_fused_supported(int n, int D, int E, int C) {
   const size_t smem = static_cast<size_t>(RPB) * (D + 2 * E + (C > 0 ? C : 0)) * sizeof(float);

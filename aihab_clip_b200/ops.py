@@ -104,3 +104,24 @@ def score(feats: torch.Tensor, proj, text_w, scale: float = 100.0, k: int = 1, w
                                  _ptr(emb), _ptr(logits), _ptr(idx), _ptr(val), _stream(dev))
     _lib.check(rc, "aihab_score")
     return emb, logits, idx, val
+
+
+def score16(feats16: torch.Tensor, proj16: torch.Tensor, text_w: torch.Tensor, scale: float = 100.0, k: int = 1,
+            want_emb: bool = False, want_logits: bool = False):
+    """Tensor-core scoring over cached 16-bit features (config 5: ProLIP / linear-probe scoring).  feats16 [n, D]
+    and proj16 [D, E] fp16 (or bf16), text_w [E, C] fp32.  Returns (emb, logits, topk_idx, topk_val) like score()."""
+    _need_cuda(feats16, proj16, text_w)
+    if feats16.dtype not in (torch.float16, torch.bfloat16) or proj16.dtype != feats16.dtype:
+        raise TypeError("score16 expects fp16 or bf16 features and projection of the same dtype")
+    f, p, w = feats16.contiguous(), proj16.contiguous(), text_w.float().contiguous()
+    n, D = f.shape
+    E, Cn = p.shape[1], w.shape[1]
+    dev = f.device
+    emb = torch.empty(n, E, dtype=torch.float32, device=dev) if want_emb else None
+    logits = torch.empty(n, Cn, dtype=torch.float32, device=dev) if want_logits else None
+    idx = torch.empty(n, k, dtype=torch.int64, device=dev) if k > 0 else None
+    val = torch.empty(n, k, dtype=torch.float32, device=dev) if k > 0 else None
+    rc = _lib.load().aihab_score16(_ptr(f), n, D, dtype_code(f.dtype), _ptr(p), E, _ptr(w), Cn, C.c_float(scale), k,
+                                   _ptr(emb), _ptr(logits), _ptr(idx), _ptr(val), _stream(dev))
+    _lib.check(rc, "aihab_score16")
+    return emb, logits, idx, val

@@ -139,6 +139,18 @@ AIHAB_API int aihab_preprocess_u8(const uint8_t* images_u8, int n, int sh, int s
 AIHAB_API int aihab_score(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C, float scale,
                 int k, float* emb_out, float* logits_out, int64_t* topk_idx, float* topk_val, void* stream);
 
+/* Same scoring over CACHED 16-bit features on the tensor cores (ProLIP / linear-probe scoring over a feature cache,
+ * methods/ProLIP.py:288-293; the reference caches features in the model dtype, fp16 on GPU — feature_cache.py:215).
+ *   feats16 : [n, D] fp16/bf16 (dtype)          proj16 : [D, E] same dtype (visual.proj after convert_weights)
+ *   text_w  : [E, C] fp32, C % 4 == 0
+ * feats16 @ proj16 runs as a tcgen05 GEMM with fp32 accumulation: products of 16-bit values are exact in fp32, so
+ * the result differs from the fp32 reference only by summation order.  The logits GEMM multiplies fp16 hi/lo splits
+ * of the normalised embedding and of the text weights (e_hi w_hi + e_hi w_lo + e_lo w_hi, relative error ~2^-21),
+ * i.e. top-k indices equal the fp32 reference's wherever its scores are untied.  Outputs as in aihab_score. */
+AIHAB_API int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj16, int E, const float* text_w,
+                            int C, float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx,
+                            float* topk_val, void* stream);
+
 /* Building blocks (exported for per-kernel parity tests; same kernels the tower uses) ---------------------- */
 /* D[M,N] = A[M,K] * W[N,K]^T with a fused epilogue; A, W 16-bit (ab_dtype), K % 8 == 0. */
 AIHAB_API int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype, int epilogue, const float* bias,

@@ -177,3 +177,31 @@ def test_topk_exact_ties(cuda_device):
     np.testing.assert_array_equal(logits.cpu().numpy(), lg)
     np.testing.assert_array_equal(idx.cpu().numpy(), O.topk_indices(lg, 4))
     assert idx[0].tolist() == [1, 2, 4, 3] and idx[1].tolist() == [0, 1, 2, 3]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n,D,E,Cn,k", [(5000, 768, 512, 1000, 5), (40000, 768, 512, 100, 3), (33, 128, 64, 20, 1)])
+def test_score16_tensor_core_path(cuda_device, dtype, n, D, E, Cn, k):
+    """Cached-feature scoring on the tensor cores: 16-bit features x 16-bit projection are exact products, the
+    logits GEMM uses an fp16 hi/lo split -> results match the fp64 reference to fp32-accumulation noise."""
+    _lib, ops = _ops()
+    rng = np.random.default_rng(n + Cn)
+    feats = torch.from_numpy(rng.standard_normal((n, D)).astype(np.float32)).to(dtype)
+    proj = torch.from_numpy((D ** -0.5 * rng.standard_normal((D, E))).astype(np.float32)).to(dtype)
+    tw = O.l2_normalize(rng.standard_normal((Cn, E)).astype(np.float32)).T.copy()
+    emb, logits, idx, val = ops.score16(feats.to(cuda_device), proj.to(cuda_device), torch.from_numpy(tw).to(cuda_device),
+                                        100.0, k, want_emb=True, want_logits=True)
+    e64 = feats.double().numpy() @ proj.double().numpy()
+    e64 /= np.maximum(np.linalg.norm(e64, axis=1, keepdims=True), 1e-12)
+    l64 = 100.0 * e64 @ tw.astype(np.float64)
+    np.testing.assert_allclose(emb.cpu().numpy(), e64, atol=3e-7, rtol=0)
+    np.testing.assert_allclose(logits.cpu().numpy(), l64, atol=3e-4, rtol=0)   # fp32 accumulation + 2^-21 split error
+    np.testing.assert_array_equal(idx.cpu().numpy(), O.topk_indices(logits.cpu().numpy(), k))
+    srt = np.sort(l64, axis=1)[:, ::-1][:, :k + 1]
+    untied = np.abs(np.diff(srt, axis=1)).min(axis=1) > 2e-3
+    assert untied.mean() > 0.9
+    np.testing.assert_array_equal(idx.cpu().numpy()[untied], O.topk_indices(l64, k)[untied])
+    # and it agrees with the exact-fp32 CUDA-core path on the same inputs
+    _, l32, i32, _ = ops.score(feats.to(cuda_device).float(), proj.to(cuda_device).float(),
+                               torch.from_numpy(tw).to(cuda_device), 100.0, k)
+    np.testing.assert_allclose(logits.cpu().numpy(), l32.cpu().numpy(), atol=5e-4, rtol=0)

@@ -72,6 +72,10 @@ def main():
     ms = time_steps(lambda: ops.score(feats, proj, tw, 100.0, 5, want_emb=False, want_logits=False), 2, warm=1)
     rows.append({"config": f"scoring {n} x 768 -> proj 512 -> 1000 classes -> top-5 (fp32 CUDA cores)",
                  "ms_per_step": round(ms, 2), "rows_per_s": round(n / ms * 1e3), "tflops": round(2.0 * n * (768 * 512 + 512 * 1000) / ms / 1e9, 2)})
+    f16, p16 = feats.half(), proj.half()
+    ms = time_steps(lambda: ops.score16(f16, p16, tw, 100.0, 5), 3, warm=1)
+    rows.append({"config": f"scoring {n} x 768 fp16 cache -> proj 512 -> 1000 classes -> top-5 (tcgen05, exact products + hi/lo split)",
+                 "ms_per_step": round(ms, 2), "rows_per_s": round(n / ms * 1e3), "tflops_algorithmic": round(2.0 * n * (768 * 512 + 512 * 1000) / ms / 1e9, 1)})
     for r in rows:
         print(json.dumps(r))
 
