@@ -142,7 +142,7 @@ class VisionTransformer(nn.Module):
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
         # engine knobs (not part of the reference protocol; defaults keep reference behaviour)
         self.compute_dtype = os.environ.get("AIHAB_CLIP_COMPUTE_DTYPE", "fp16")
-        self.max_batch = int(os.environ.get("AIHAB_CLIP_MAX_BATCH", "128"))
+        self.max_batch = int(os.environ.get("AIHAB_CLIP_MAX_BATCH", "256"))
         self._engine = None
         self._engine_key = None
 

@@ -135,6 +135,17 @@ void keep_pool_warm(int dev) {
   done[dev] = true;
 }
 
+// CTA-pair (tcgen05 cta_group::2) GEMM tiles: AIHAB_GEMM_PAIR=1/0 forces them on/off, default = gemm_use_pair()
+bool gemm_pair_enabled(int M, int N, int sms) {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("AIHAB_GEMM_PAIR");
+    v = (e != nullptr) ? (e[0] != '0') : -1;
+  }
+  if (v >= 0) return v != 0 && aihab::gemm_block_n(M, N, sms) == 256;
+  return aihab::gemm_use_pair(M, N, sms);
+}
+
 int sm_count(int dev) {
   static std::mutex mu;
   static std::map<int, int> cache;
@@ -401,9 +412,10 @@ int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], in
   p.reverse_m = 0;
   const int bn = aihab::gemm_block_n(M, N, h->num_sms);
   if (n_blocks_out) *n_blocks_out = (N + bn - 1) / bn;
+  const bool pair = gemm_pair_enabled(M, N, h->num_sms);  // a pair stages the 256-wide W tile as two 128-row halves
   ProfScope ps(PC_GEMM, 2.0 * M * N * K, s);
-  CKL(aihab::launch_gemm(ma, mw[bn == 256 ? 1 : 0], epi == aihab::EPI_BIAS_RES_32 ? &h->m_x : nullptr, p, bn,
-                         h->num_sms, s));
+  CKL(aihab::launch_gemm(ma, mw[(bn == 256 && !pair) ? 1 : 0], epi == aihab::EPI_BIAS_RES_32 ? &h->m_x : nullptr, p, bn,
+                         h->num_sms, s, pair));
   return 0;
 }
 
@@ -846,8 +858,9 @@ int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype
   const int sms = sm_count(dev);
   const int bn = aihab::gemm_block_n(M, N, sms);
   CUtensorMap ma, mw;
+  const bool pair = gemm_pair_enabled(M, N, sms);
   CK(aihab::make_tmap_2d_16bit(&ma, A, M, K, static_cast<uint64_t>(K) * 2, 128, bf16));
-  CK(aihab::make_tmap_2d_16bit(&mw, W, N, K, static_cast<uint64_t>(K) * 2, bn, bf16));
+  CK(aihab::make_tmap_2d_16bit(&mw, W, N, K, static_cast<uint64_t>(K) * 2, pair ? 128 : bn, bf16));
   aihab::GemmParams p{};
   p.M = M;
   p.N = N;
@@ -868,7 +881,7 @@ int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype
     if (out32 == nullptr || (N & 31)) return fail("aihab_gemm16: EPI_BIAS_RES_32 needs out32 and N % 32 == 0");
     CK(aihab::make_tmap_2d_f32_box32(&mc, out32, M, N, static_cast<uint64_t>(ldo) * 4));
   }
-  CKL(aihab::launch_gemm(ma, mw, res ? &mc : nullptr, p, bn, sms, static_cast<cudaStream_t>(stream)));
+  CKL(aihab::launch_gemm(ma, mw, res ? &mc : nullptr, p, bn, sms, static_cast<cudaStream_t>(stream), pair));
   return 0;
 }
 

@@ -67,11 +67,15 @@ cudaError_t make_tmap_2d_f32_box32(CUtensorMap* map, const void* base, uint64_t 
 
 // Launches the GEMM.  tmap_a box = {64,128}; tmap_w box = {64,BN} with BN = gemm_block_n(N, M);
 // tmap_c (EPI_BIAS_RES_32 only, N % 32 == 0) = make_tmap_2d_f32_box32 over out32.
+// pair = true (block_n must be 256, tmap_w box = {64,128}): CTA pairs with tcgen05 cta_group::2 (UMMA M = 256).
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, const CUtensorMap* tmap_c,
-                        const GemmParams& p, int block_n, int num_sms, cudaStream_t stream);
+                        const GemmParams& p, int block_n, int num_sms, cudaStream_t stream, bool pair = false);
 
 // Tile-N policy shared by map construction and launch.
 int gemm_block_n(int M, int N, int num_sms);
+// CTA-pair policy: true when 256-wide tiles are used and pairing M blocks does not cost more in wave quantisation
+// than the ~5 % it gains per tile.
+bool gemm_use_pair(int M, int N, int num_sms);
 
 cudaError_t gemm_init();  // sets max dynamic smem attributes; resolves cuTensorMapEncodeTiled
 

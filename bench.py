@@ -375,7 +375,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arch", default="ViT-B/16")
-    ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--classes", type=int, default=20)
     ap.add_argument("--ref-batch", type=int, default=8, help="--impl reference: images per step (bounded sample)")
