@@ -124,3 +124,23 @@ def test_errors_are_python_exceptions(tmp_path, cuda_device):
     import aihab_clip_b200.clip as clip
     with pytest.raises(RuntimeError):
         clip.load("/nonexistent/model.pt")
+
+
+def test_large_batch_uses_cta_pairs_and_matches_small_batches(tmp_path, cuda_device):
+    """At 256+ images the 256-wide GEMM tiles run as CTA pairs (tcgen05 cta_group::2) and the LayerNorm fold is
+    active; per-image results must still equal those of small batches bit for bit, and match the oracle."""
+    geom = GEOMETRIES["ViT-tiny/14"]
+    _, model, preprocess = load_model(tmp_path, geom.name, 1, cuda_device)
+    model.float()
+    u8 = torch.from_numpy(synthetic_images_u8(300, 111)).to(cuda_device)
+    x = preprocess.batch_u8(u8)
+    model.visual.max_batch = 256
+    big = model.encode_image(x)               # chunks of 256 + 44 images
+    model.visual.max_batch = 7
+    small = model.encode_image(x[:21])        # three chunks of 7
+    assert torch.equal(big[:21], small)
+    assert torch.equal(model.encode_image(x[280:300]), big[280:300])
+    sd = make_state_dict_np(geom, 1, with_text=False)
+    ref = O.encode_image(sd, x[:4].cpu().numpy())
+    assert cosine(big[:4].cpu().numpy(), ref).min() >= 0.999
+    np.testing.assert_allclose(big[:4].cpu().numpy(), ref, atol=1e-2, rtol=0)
