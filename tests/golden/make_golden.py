@@ -203,6 +203,23 @@ def main():
     meta["cache_backbone_names"] = {b: _canonical_backbone_name(b) for b in
                                     ["ViT-B/16", "ViT-B/32", "ViT-L/14", "RN50", "", "hf-hub:timm/x y:z"]}
 
+    # ---- large agreement set (BASELINE.json gate: zero-shot argmax agreement >= 99.9 %): 4096 images, ViT-B/32,
+    # 224 px inputs (no resize), 20 shipped classes; logits stored so that max |dlogit| is measured on the same set
+    _, state32, model32, _ = load_reference_model(ref_clip, "ViT-B/32", 0)
+    n_agree = 4096
+    u8 = np.concatenate([synthetic_images_u8(n_agree // 2, 224, seed=777),
+                         synthetic_images_u8(n_agree // 2, 224, seed=777, start=n_agree // 2, smooth=True)])
+    tw = torch.from_numpy(gold["b32_text_w"])
+    chunks = []
+    with torch.no_grad():
+        for i in range(0, n_agree, 64):
+            x = ref_preprocess(u8[i:i + 64], 224)
+            f = model32.encode_image(x)
+            emb = F.normalize(f @ state32["visual.proj"], dim=-1)
+            chunks.append((100. * emb @ tw).numpy())
+    gold["agree_logits"] = np.concatenate(chunks).astype(np.float32)
+    print("agreement set:", gold["agree_logits"].shape, "classes hit:", np.unique(gold["agree_logits"].argmax(1)).size)
+
     np.savez_compressed(HERE / "reference_outputs.npz", **gold)
     (HERE / "reference_meta.json").write_text(json.dumps(meta, indent=1))
     print("wrote", HERE / "reference_outputs.npz", (HERE / "reference_outputs.npz").stat().st_size, "bytes")

@@ -144,3 +144,32 @@ def test_large_batch_uses_cta_pairs_and_matches_small_batches(tmp_path, cuda_dev
     ref = O.encode_image(sd, x[:4].cpu().numpy())
     assert cosine(big[:4].cpu().numpy(), ref).min() >= 0.999
     np.testing.assert_allclose(big[:4].cpu().numpy(), ref, atol=1e-2, rtol=0)
+
+
+def test_zero_shot_agreement_on_4096_images(tmp_path, cuda_device, gold, capsys):
+    """BASELINE.json gates on a statistically meaningful set: 4096 synthetic images (half noise, half smooth),
+    ViT-B/32, 20 classes, reference logits from the unmodified reference (tests/golden/make_golden.py)."""
+    from aihab_clip_b200 import ops
+    geom = GEOMETRIES["ViT-B/32"]
+    _, model, _ = load_model(tmp_path, geom.name, 0, cuda_device)
+    model.float()
+    n = 4096
+    u8 = np.concatenate([synthetic_images_u8(n // 2, 224, seed=777),
+                         synthetic_images_u8(n // 2, 224, seed=777, start=n // 2, smooth=True)])
+    feats = model.encode_image_u8(torch.from_numpy(u8).to(cuda_device))
+    _, logits, idx, _ = ops.score(feats, model.visual.proj, torch.from_numpy(gold["b32_text_w"]).to(cuda_device), 100.0, 3)
+    got, ref = logits.cpu().numpy(), gold["agree_logits"]
+    err = float(np.abs(got - ref).max())
+    srt = np.sort(ref, axis=1)[:, ::-1]
+    margin = srt[:, 0] - srt[:, 1]
+    agree = idx[:, 0].cpu().numpy() == ref.argmax(1)
+    near_tie = margin < 2 * err
+    with capsys.disabled():
+        print(f"\n[agreement] n={n} max|dlogit|={err:.2e} strict argmax agreement={agree.mean() * 100:.3f}% "
+              f"reference near-ties (margin < 2 err)={int(near_tie.sum())} untied agreement="
+              f"{agree[~near_tie].mean() * 100:.3f}% disagreements among untied={int((~agree[~near_tie]).sum())}")
+    assert err <= 1e-2
+    assert agree[~near_tie].all(), "an untied zero-shot prediction differs from the reference"
+    assert agree.mean() >= 0.999 or (~agree).sum() <= near_tie.sum()
+    untied3 = np.abs(np.diff(srt[:, :4], axis=1)).min(axis=1) > 2 * err
+    np.testing.assert_array_equal(idx.cpu().numpy()[untied3], np.argsort(-ref, axis=1, kind="stable")[untied3, :3])

@@ -103,3 +103,16 @@ def test_text_head_18x80_shape(gold):
     w = gold["b32_text_w_18x80"]
     assert w.shape == (512, 18)
     np.testing.assert_allclose(np.linalg.norm(w, axis=0), 1.0, atol=1e-5)
+
+
+def test_agreement_set_subset_matches_oracle(gold):
+    """First 32 noise + 32 smooth images of the 4096-image agreement set through the oracle."""
+    geom = GEOMETRIES["ViT-B/32"]
+    sd = make_state_dict_np(geom, 0, with_text=False)
+    n = 4096
+    u8 = np.concatenate([synthetic_images_u8(16, 224, seed=777),
+                         synthetic_images_u8(16, 224, seed=777, start=n // 2, smooth=True)])
+    x = np.stack([O.clip_preprocess(im, 224) for im in u8])
+    _, logits, _ = O.score(O.encode_image(sd, x), sd["visual.proj"], gold["b32_text_w"], 100.0, 1)
+    ref = np.concatenate([gold["agree_logits"][:16], gold["agree_logits"][n // 2:n // 2 + 16]])
+    np.testing.assert_allclose(logits, ref, atol=1e-3, rtol=0)
