@@ -302,6 +302,7 @@ struct aihab_vit {
   void* y2 = nullptr;       // [cap_rows, D] 16-bit: gamma * x written by the residual epilogues (LayerNorm fold)
   float* ln_stats = nullptr;  // [cap_rows, kMaxStatBlocks, 2] per-tile (sum, sum sq) partials of the residual rows
   bool ln_fold = true;
+  bool zigzag = true;  // consecutive kernels walk the rows in opposite directions (L2 keeps the producer's last rows)
   CUtensorMap m_y2;
   CUtensorMap m_patches, m_y, m_h, m_x;  // m_x: fp32 residual stream, {32,32} boxes (EPI_BIAS_RES_32)
   CUtensorMap m_attn_q, m_attn_kv;       // qkv view [cap_rows, 3D] of `big` for the tcgen05 attention
@@ -389,7 +390,7 @@ struct LnOpt {
 
 int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], int M, int N, int K, int epi,
              const float* bias, void* out16, float* out32, int ldo, cudaStream_t s, const LnOpt& ln = LnOpt(),
-             int* n_blocks_out = nullptr) {
+             int* n_blocks_out = nullptr, int reverse = 0) {
   aihab::GemmParams p{};
   p.ln_gamma = ln.gamma;
   p.a16_out = ln.gamma ? h->y2 : nullptr;
@@ -409,7 +410,7 @@ int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], in
   p.pos = h->pos;
   p.g2 = h->g2;
   p.scale = 1.0f;
-  p.reverse_m = 0;
+  p.reverse_m = reverse;
   const int bn = aihab::gemm_block_n(M, N, h->num_sms);
   if (n_blocks_out) *n_blocks_out = (N + bn - 1) / bn;
   const bool pair = gemm_pair_enabled(M, N, h->num_sms);  // a pair stages the 256-wide W tile as two 128-row halves
@@ -432,6 +433,14 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
   }
   const int layers = static_cast<int>(h->blocks.size());
   int nsb = 0;  // stat blocks per row written by the last residual GEMM
+  // Zig-zag traversal: each kernel walks the token rows in the direction opposite to its producer, so the ~100 MB the
+  // producer wrote last are still in the 126 MB L2 when the consumer reads them first (results do not depend on order).
+  int dir = 0;
+  auto next_dir = [&]() {
+    const int d = h->zigzag ? dir : 0;
+    dir ^= 1;
+    return d;
+  };
   for (int l = 0; l < layers; ++l) {
     aihab_vit::Block& b = h->blocks[l];
     // x = x + out_proj(attn(in_proj(ln_1(x))))   (clip/model.py:181,184)
@@ -440,17 +449,22 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
         ProfScope ps(PC_LN, 6.0 * M * D, s);
         CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln1_g, b.ln1_b, nullptr, h->y2, h->bf16, M, D, s));
       }
-      if (run_gemm(h, h->m_y2, b.m_in, M, 3 * D, D, aihab::EPI_BIAS_16, b.b_in, h->big, nullptr, 3 * D, s)) return 1;
+      if (run_gemm(h, h->m_y2, b.m_in, M, 3 * D, D, aihab::EPI_BIAS_16, b.b_in, h->big, nullptr, 3 * D, s, LnOpt(), nullptr,
+                   next_dir()))
+        return 1;
     } else {  // ln_1 folded: y2 = gamma_1 * x and the row statistics came out of the previous c_proj epilogue
       LnOpt o;
       o.s = b.s_in;
       o.nsb = nsb;
-      if (run_gemm(h, h->m_y2, b.m_in, M, 3 * D, D, aihab::EPI_LN_BIAS_16, b.bp_in, h->big, nullptr, 3 * D, s, o)) return 1;
+      if (run_gemm(h, h->m_y2, b.m_in, M, 3 * D, D, aihab::EPI_LN_BIAS_16, b.bp_in, h->big, nullptr, 3 * D, s, o, nullptr,
+                   next_dir()))
+        return 1;
     }
     {
       ProfScope ps(PC_ATTN, 4.0 * n * L * L * D, s);
       if (h->attn_kind == 2)
-        CKL(aihab::launch_attention_tcp(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, h->num_sms, s));
+        CKL(aihab::launch_attention_tcp(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, h->num_sms, s,
+                                        next_dir()));
       else if (h->attn_kind == 1)
         CKL(aihab::launch_attention_tc(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, s));
       else
@@ -459,7 +473,8 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
     {
       LnOpt o;
       if (h->ln_fold) o.gamma = b.ln2_g;
-      if (run_gemm(h, h->m_y, b.m_out, M, D, D, aihab::EPI_BIAS_RES_32, b.b_out, nullptr, h->x, D, s, o, &nsb)) return 1;
+      if (run_gemm(h, h->m_y, b.m_out, M, D, D, aihab::EPI_BIAS_RES_32, b.b_out, nullptr, h->x, D, s, o, &nsb, next_dir()))
+        return 1;
     }
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))   (clip/model.py:171-175,185)
     if (!h->ln_fold) {
@@ -467,18 +482,22 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
         ProfScope ps(PC_LN, 6.0 * M * D, s);
         CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln2_g, b.ln2_b, nullptr, h->y2, h->bf16, M, D, s));
       }
-      if (run_gemm(h, h->m_y2, b.m_fc, M, 4 * D, D, aihab::EPI_BIAS_GELU_16, b.b_fc, h->big, nullptr, 4 * D, s)) return 1;
+      if (run_gemm(h, h->m_y2, b.m_fc, M, 4 * D, D, aihab::EPI_BIAS_GELU_16, b.b_fc, h->big, nullptr, 4 * D, s, LnOpt(),
+                   nullptr, next_dir()))
+        return 1;
     } else {
       LnOpt o;
       o.s = b.s_fc;
       o.nsb = nsb;
-      if (run_gemm(h, h->m_y2, b.m_fc, M, 4 * D, D, aihab::EPI_LN_BIAS_GELU_16, b.bp_fc, h->big, nullptr, 4 * D, s, o))
+      if (run_gemm(h, h->m_y2, b.m_fc, M, 4 * D, D, aihab::EPI_LN_BIAS_GELU_16, b.bp_fc, h->big, nullptr, 4 * D, s, o, nullptr,
+                   next_dir()))
         return 1;
     }
     {
       LnOpt o;
       if (h->ln_fold && l + 1 < layers) o.gamma = h->blocks[l + 1].ln1_g;  // the last block feeds ln_post (kernel)
-      if (run_gemm(h, h->m_h, b.m_proj, M, D, 4 * D, aihab::EPI_BIAS_RES_32, b.b_proj, nullptr, h->x, D, s, o, &nsb)) return 1;
+      if (run_gemm(h, h->m_h, b.m_proj, M, D, 4 * D, aihab::EPI_BIAS_RES_32, b.b_proj, nullptr, h->x, D, s, o, &nsb, next_dir()))
+        return 1;
     }
   }
   // ln_post on token 0 of every image (clip/model.py:228); rows are L*D apart
@@ -599,6 +618,8 @@ int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, in
   {
     const char* e = getenv("AIHAB_LNFOLD");
     h->ln_fold = !(e && e[0] == '0') && D / 128 <= kMaxStatBlocks;
+    const char* z = getenv("AIHAB_ZIGZAG");
+    h->zigzag = !(z && z[0] == '0');
   }
   h->blocks.resize(cfg->layers);
   for (int i = 0; i < cfg->layers; ++i) {
@@ -874,7 +895,7 @@ int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype
   p.pos = pos;
   p.g2 = g2;
   p.scale = scale;
-  if (const char* dbg = getenv("AIHAB_GEMM_DEBUG")) p.reverse_m = atoi(dbg);  // 77 no epilogue, 78 TMEM loads only, 79 no stores
+  if (const char* dbg = getenv("AIHAB_GEMM_DEBUG")) p.debug = atoi(dbg);  // 77: no 16-bit epilogue (main-loop ceiling)
   CUtensorMap mc;
   const bool res = epilogue == AIHAB_EPI_BIAS_RES_32;
   if (res) {

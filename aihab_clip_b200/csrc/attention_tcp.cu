@@ -95,7 +95,7 @@ __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L,
 template <bool BF16, int NC>
 __global__ void __launch_bounds__(P_THREADS, 1)
 attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                     uint16_t* __restrict__ out, int L, int H, int Lk, int nq, int total) {
+                     uint16_t* __restrict__ out, int L, int H, int Lk, int nq, int total, int reverse) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -125,6 +125,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       u = idx >> 1;
       qt = (idx & 1) ^ (it & 1);
     }
+    if (reverse) u = total / nq - 1 - u;  // walk (image, head) units from the end: the producer's freshest rows first
     img = u / H;
     h = u - img * H;
   };
@@ -276,26 +277,26 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
 template <bool BF16, int NC>
 cudaError_t launch_nc(const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* out, int L, int H, int Lk, int nq,
-                      int total, int grid, cudaStream_t stream) {
+                      int total, int grid, int reverse, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_tcp_kernel<BF16, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  attention_tcp_kernel<BF16, NC><<<grid, P_THREADS, P_SMEM, stream>>>(tq, tkv, out, L, H, Lk, nq, total);
+  attention_tcp_kernel<BF16, NC><<<grid, P_THREADS, P_SMEM, stream>>>(tq, tkv, out, L, H, Lk, nq, total, reverse);
   return cudaGetLastError();
 }
 
 template <bool BF16>
 cudaError_t launch_dt(int nc, const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* out, int L, int H, int Lk,
-                      int nq, int total, int grid, cudaStream_t stream) {
+                      int nq, int total, int grid, int reverse, cudaStream_t stream) {
   switch (nc) {
-    case 3: return launch_nc<BF16, 3>(tq, tkv, out, L, H, Lk, nq, total, grid, stream);
-    case 4: return launch_nc<BF16, 4>(tq, tkv, out, L, H, Lk, nq, total, grid, stream);
-    case 5: return launch_nc<BF16, 5>(tq, tkv, out, L, H, Lk, nq, total, grid, stream);
-    case 6: return launch_nc<BF16, 6>(tq, tkv, out, L, H, Lk, nq, total, grid, stream);
-    case 7: return launch_nc<BF16, 7>(tq, tkv, out, L, H, Lk, nq, total, grid, stream);
+    case 3: return launch_nc<BF16, 3>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
+    case 4: return launch_nc<BF16, 4>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
+    case 5: return launch_nc<BF16, 5>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
+    case 6: return launch_nc<BF16, 6>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
+    case 7: return launch_nc<BF16, 7>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -305,7 +306,7 @@ cudaError_t launch_dt(int nc, const CUtensorMap& tq, const CUtensorMap& tkv, uin
 bool attention_tcp_supported(int L) { return L > 64 && (L + 15) / 16 * 16 <= KV_MAX; }
 
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
-                                 int H, int is_bf16, int num_sms, cudaStream_t stream) {
+                                 int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse) {
   if (n_img <= 0) return cudaSuccess;
   if (!attention_tcp_supported(L)) return cudaErrorInvalidValue;
   const int Lk = (L + 15) / 16 * 16;
@@ -315,8 +316,8 @@ cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& t
   if (nq == 2) grid &= ~1;  // even: a CTA's items alternate between the full and the partial query tile
   const int nc = ((Lk >> 4) + 1) >> 1;
   uint16_t* o = static_cast<uint16_t*>(out);
-  return is_bf16 ? launch_dt<true>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, stream)
-                 : launch_dt<false>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, stream);
+  return is_bf16 ? launch_dt<true>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream)
+                 : launch_dt<false>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream);
 }
 
 }  // namespace aihab

@@ -43,6 +43,7 @@ struct GemmParams {
   int g2;             // EPI_PATCH_32: patches per image (L = g2 + 1)
   float scale;        // EPI_SCALE_32
   int reverse_m;      // walk M blocks from last to first (L2 reuse of the producer's freshest rows)
+  int debug;          // 0 = normal; 77 = skip the 16-bit epilogues entirely (main-loop ceiling measurement, AIHAB_GEMM_DEBUG)
   // EPI_BIAS_RES_32 as LayerNorm PRODUCER (optional, ln_gamma != nullptr): besides updating the residual it stores
   //   a16_out[m,n] = round16(ln_gamma[n] * x_new[m,n])            (A operand of the next GEMM, ld = N)
   //   stats_out[m, n_blk, 0..1] = (sum, sum of squares) of x_new over this tile's columns (deterministic order)

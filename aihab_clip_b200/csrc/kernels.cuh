@@ -42,7 +42,7 @@ cudaError_t launch_attention_tc(const CUtensorMap& tmap_q, const CUtensorMap& tm
 // epilogue of item i-1 overlapped with the PV MMA.  Same tensor maps as launch_attention_tc.
 bool attention_tcp_supported(int L);
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
-                                 int H, int is_bf16, int num_sms, cudaStream_t stream);
+                                 int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse = 0);
 
 // fp32 -> 16-bit cast of a weight matrix [rows, cols] into [rows, cols_pad] (zero padded columns).
 cudaError_t launch_cast_pad(const float* src, int rows, int cols, void* dst, int cols_pad, int out_bf16,
