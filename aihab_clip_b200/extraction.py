@@ -117,8 +117,10 @@ class ShardedExtractor:
         compute = torch.cuda.current_stream(dev)
         starts = list(range(lo, hi, self.batch))
         host_out = None
-        if self.copy_results_to_host:
-            host_out = torch.empty(per, E + 1, dtype=torch.float32, pin_memory=True)
+        if self.copy_results_to_host:  # pinned result buffer is cached: cudaHostAlloc is slow and must not sit in the loop
+            if getattr(self, "_host_out", None) is None or tuple(self._host_out.shape) != (per, E + 1):
+                self._host_out = torch.empty(per, E + 1, dtype=torch.float32, pin_memory=True)
+            host_out = self._host_out
 
         def stage(i):
             b0 = starts[i]
