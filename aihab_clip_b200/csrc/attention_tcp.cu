@@ -64,7 +64,8 @@ __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L,
   }
   // after this barrier every S column of the tile has been read into registers: P may overwrite S in place
   ptx::tc_fence_before();
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  // only the two warps that share this lane quadrant (the two column halves of the same 32 rows) have to meet
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + (row >> 5)) : "memory");
   ptx::tc_fence_after();
   if (has_rows) {
     const float ms = fmaxf(s_max_b[row], s_max_b[128 + row]) * sl2;

@@ -48,8 +48,19 @@ struct SmemLayout {
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
-  // x * sigmoid(1.702 x)  (clip/model.py:160-162), fp32 with ex2/rcp approximations (<= 2 ulp each)
+  // x * sigmoid(1.702 x)  (clip/model.py:160-162)
+#ifdef AIHAB_GELU_EXACT
+  // ex2 + rcp (<= 2 ulp each): two MUFU operations per element
   return __fdividef(x, 1.0f + __expf(-1.702f * x));
+#else
+  // sigmoid(z) = 0.5 + 0.5 tanh(z / 2) with tanh.approx.f32 (max relative error 2^-11, i.e. at the precision of the
+  // 16-bit value this feeds): ONE MUFU operation per element - the c_fc epilogue is MUFU-bound (32768 elements / tile).
+  // CPU emulation of the whole tower with a 2^-11 tanh error moves max |dlogit| from 3.0e-3 to <= 3.8e-3.
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+#endif
 }
 
 // TWO = CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, UMMA M = 256; each CTA loads its own
