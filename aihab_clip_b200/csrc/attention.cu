@@ -166,7 +166,7 @@ attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, i
   }
 }
 
-int g_attn_max_smem = 0;
+int g_attn_max_smem[64] = {};  // per device: cudaFuncSetAttribute is a per-device setting
 
 }  // namespace
 
@@ -174,12 +174,15 @@ cudaError_t attention_init(int max_L) {
   const int Lp = (max_L + 63) / 64 * 64;
   const int smem = Lp * 256;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  if (smem <= g_attn_max_smem) return cudaSuccess;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (smem <= g_attn_max_smem[dev]) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  g_attn_max_smem = smem;
+  g_attn_max_smem[dev] = smem;
   return cudaSuccess;
 }
 
@@ -188,8 +191,8 @@ cudaError_t launch_attention(const void* qkv, void* out, int n_img, int L, int H
   if (L <= 0 || H <= 0) return cudaErrorInvalidValue;
   const int Lp = (L + 63) / 64 * 64;
   const int smem = Lp * 256;
-  if (smem > g_attn_max_smem) {
-    cudaError_t e = attention_init(L);
+  {
+    cudaError_t e = attention_init(L);  // no-op once this device's limit covers the request
     if (e != cudaSuccess) return e;
   }
   const int q_tiles = (L + 15) / 16;

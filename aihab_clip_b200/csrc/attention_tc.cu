@@ -211,7 +211,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
-bool g_tc_init = false;
+bool g_tc_init[64] = {};  // per device
 
 }  // namespace
 
@@ -223,12 +223,15 @@ cudaError_t launch_attention_tc(const CUtensorMap& tmap_q, const CUtensorMap& tm
                                 int H, int is_bf16, cudaStream_t stream) {
   if (n_img <= 0) return cudaSuccess;
   if (!attention_tc_supported(L)) return cudaErrorInvalidValue;
-  if (!g_tc_init) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!g_tc_init[dev]) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e != cudaSuccess) return e;
-    g_tc_init = true;
+    g_tc_init[dev] = true;
   }
   const int Lk = attention_tc_key_rows(L);
   dim3 grid((L + 127) / 128, H, n_img);

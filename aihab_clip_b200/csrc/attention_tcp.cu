@@ -279,11 +279,14 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 template <bool BF16, int NC>
 cudaError_t launch_nc(const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* out, int L, int H, int Lk, int nq,
                       int total, int grid, int reverse, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(attention_tcp_kernel<BF16, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   attention_tcp_kernel<BF16, NC><<<grid, P_THREADS, P_SMEM, stream>>>(tq, tkv, out, L, H, Lk, nq, total, reverse);
   return cudaGetLastError();
