@@ -55,6 +55,9 @@ GEOMETRIES = {
     "ViT-L/14@336px": Geometry("ViT-L/14@336px", 768, 336, 24, 1024, 14, 77, 49408, 768, 12, 12),
     "ViT-tiny/16": Geometry("ViT-tiny/16", 64, 64, 2, 128, 16, 77, 49408, 64, 1, 2),
     "ViT-tiny/14": Geometry("ViT-tiny/14", 128, 56, 3, 256, 14, 77, 49408, 64, 1, 1),
+    # ViT-L/14 widths and sequence lengths (257 / 577 tokens) with 2 blocks only: parity cases for configs 3 and 4
+    "ViT-L-mini/14": Geometry("ViT-L-mini/14", 768, 224, 2, 1024, 14, 77, 49408, 64, 1, 1),
+    "ViT-L-mini/14@336px": Geometry("ViT-L-mini/14@336px", 768, 336, 2, 1024, 14, 77, 49408, 64, 1, 1),
 }
 
 

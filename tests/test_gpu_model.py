@@ -173,3 +173,21 @@ def test_zero_shot_agreement_on_4096_images(tmp_path, cuda_device, gold, capsys)
     assert agree.mean() >= 0.999 or (~agree).sum() <= near_tie.sum()
     untied3 = np.abs(np.diff(srt[:, :4], axis=1)).min(axis=1) > 2 * err
     np.testing.assert_array_equal(idx.cpu().numpy()[untied3], np.argsort(-ref, axis=1, kind="stable")[untied3, :3])
+
+
+@pytest.mark.parametrize("geom_name,n", [("ViT-L-mini/14", 5), ("ViT-L-mini/14@336px", 3)])
+def test_vit_l_geometries_match_oracle(tmp_path, cuda_device, geom_name, n):
+    """ViT-L/14 shapes (width 1024, 16 heads, 588 -> 640 padded patch K, 257 / 577 tokens) against the numpy oracle
+    (2 blocks keep the CPU side fast; BASELINE.json configs 3 and 4 are parity cases)."""
+    geom = GEOMETRIES[geom_name]
+    _, model, preprocess = load_model(tmp_path, geom.name, 3, cuda_device)
+    model.float()
+    u8 = synthetic_images_u8(n, 300, smooth=True)
+    x = preprocess.batch_u8(torch.from_numpy(u8).to(cuda_device))
+    R = geom.image_resolution
+    ref_x = np.stack([O.clip_preprocess(im, R) for im in u8])
+    np.testing.assert_array_equal(x.cpu().numpy(), ref_x)
+    feats = model.encode_image(x).cpu().numpy()
+    ref = O.encode_image(make_state_dict_np(geom, 3, with_text=False), ref_x)
+    assert cosine(feats, ref).min() >= 0.999
+    np.testing.assert_allclose(feats, ref, atol=1e-2, rtol=0)
