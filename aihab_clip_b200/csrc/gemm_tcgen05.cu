@@ -30,10 +30,12 @@ struct SmemLayout {
   // read-modify-write, not by the MMA pipe.  In a CTA pair each CTA stages only half of the W tile.
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
-  static constexpr int kStages = TWO ? (kRes ? 4 : 6) : ((BN == 256) ? (kRes ? 3 : 4) : (kRes ? 4 : 6));
+  static constexpr bool kOut16 = epi_out16(EPI);
+  static constexpr int kStages =
+      TWO ? (kRes ? 4 : (kOut16 ? 5 : 6)) : ((BN == 256) ? ((kRes || kOut16) ? 3 : 4) : (kRes ? 4 : (kOut16 ? 5 : 6)));
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // residual ring (4 warps x RS boxes) + 4 x 2 KB for the coalesced gamma*x store | 8 or 4 warps x staging tile
-  static constexpr int kStagingBytes = kRes ? 4 * RS * RES_BOX + 4 * 2048 : (epi_out16(EPI) ? 8 * 2048 : 4 * 4096);
+  // residual ring (4 warps x RS boxes) + 4 x 2 KB for the coalesced gamma*x store | 8 or 4 warps x 4 KB staging tile
+  static constexpr int kStagingBytes = kRes ? 4 * RS * RES_BOX + 4 * 2048 : (kOut16 ? 8 * 4096 : 4 * 4096);
   static constexpr int kBiasBytes = 4 * BN * 4;  // [2][BN] bias + [2][BN] auxiliary per-column vector (s_n / gamma)
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kStages * kABytes;
@@ -220,7 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr int kEpiThreads = epi_warps(EPI) * 32;
     const int ew = warp & 3;                   // TMEM lanes [32*ew, 32*ew+32) (hardware: warp % 4)
     const int ehalf = (warp - EPI_WARP0) >> 2;  // 0, or 0/1 when two warps share a quadrant
-    uint8_t* stg = sStaging + (kOut16 ? (warp - EPI_WARP0) * 2048 : ew * 4096);
+    uint8_t* stg = sStaging + (kOut16 ? (warp - EPI_WARP0) * 4096 : ew * 4096);
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..kEpiThreads-1
     const bool bf16 = p.ab_format != 0;
     // EPI_BIAS_RES_32: every warp streams its 32-row slice of the fp32 residual through a private ring of 4 KB
@@ -299,22 +301,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
 
       if constexpr (kOut16) {
-        // 32-column chunks, dealt alternately to the two warps of a lane quadrant
+        // 64-column chunks, dealt alternately to the two warps of a lane quadrant.  A chunk leaves as ONE TMA store of
+        // a 32-row x 128-byte box: the staging tile is written in the SWIZZLE_128B pattern (16-byte units XOR row & 7,
+        // conflict-free), the store writes complete 128-byte lines and clips the M / N tails itself.
 #pragma unroll 1
-        for (int c = ehalf; c < BN / 32; c += 2) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, r);
+        for (int c = ehalf; c < BN / 64; c += 2) {
+          uint32_t ra[32], rb[32];
+          ptx::tmem_ld_32x32(taddr + c * 64, ra);
+          ptx::tmem_ld_32x32(taddr + c * 64 + 32, rb);
           ptx::tmem_ld_wait();
-          uint32_t pk[16];
+          if (c + 2 >= BN / 64) {  // last chunk of this warp: the accumulator stage can go back to the MMA issuer now
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (TWO) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
+              else ptx::mbar_arrive(&tmem_empty_bar[as]);
+            }
+          }
+          const float* cb = sb + c * 64;
+          const float* cx = sx + c * 64;
+          uint32_t pk[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 32; ++j) {
+            const float v0 = __uint_as_float(j < 16 ? ra[2 * j] : rb[2 * j - 32]);
+            const float v1 = __uint_as_float(j < 16 ? ra[2 * j + 1] : rb[2 * j - 31]);
             float a0, a1;
             if constexpr (kLn) {
-              a0 = fmaf(ln_r, __uint_as_float(r[2 * j]), fmaf(ln_nrm, sx[c * 32 + 2 * j], sb[c * 32 + 2 * j]));
-              a1 = fmaf(ln_r, __uint_as_float(r[2 * j + 1]), fmaf(ln_nrm, sx[c * 32 + 2 * j + 1], sb[c * 32 + 2 * j + 1]));
+              a0 = fmaf(ln_r, v0, fmaf(ln_nrm, cx[2 * j], cb[2 * j]));
+              a1 = fmaf(ln_r, v1, fmaf(ln_nrm, cx[2 * j + 1], cb[2 * j + 1]));
             } else {
-              a0 = __uint_as_float(r[2 * j]) + sb[c * 32 + 2 * j];
-              a1 = __uint_as_float(r[2 * j + 1]) + sb[c * 32 + 2 * j + 1];
+              a0 = v0 + cb[2 * j];
+              a1 = v1 + cb[2 * j + 1];
             }
             if constexpr (kGelu) {
               a0 = quick_gelu(a0);
@@ -322,27 +339,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             pk[j] = bf16 ? ptx::pack2<true>(a0, a1) : ptx::pack2<false>(a0, a1);
           }
-          // transpose through a 32 x 64 B staging tile (16 B units XOR-swizzled by (row >> 1) & 3: conflict-free both
-          // ways) so that every global store instruction writes 8 complete 64 B row segments
+          if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store of this warp has finished reading the tile
+          __syncwarp();
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) =
+          for (int u = 0; u < 8; ++u) {
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) =
                 make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
           }
+          ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
           __syncwarp();
-          const int u = lane & 3;
-          const int gcol = n0 + c * 32 + u * 8;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = i * 8 + (lane >> 2);
-            const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 64 + ((u ^ ((row >> 1) & 3)) << 4));
-            const int grow = m0 + row;
-            if (grow < p.M && gcol < p.N) {
-              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + static_cast<size_t>(grow) * p.ldo +
-                                        gcol) = v;
-            }
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_c, stg, n0 + c * 64, m0);
+            ptx::bulk_commit();
           }
-          __syncwarp();
         }
       } else if constexpr (EPI == EPI_BIAS_RES_32) {
         float ln_s1 = 0.f, ln_s2 = 0.f;  // LayerNorm producer: this row's sum / sum of squares over the tile
@@ -467,15 +476,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           __syncwarp();
         }
       }
-      // accumulator stage drained: hand it back to the MMA issuer
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (TWO) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);  // the leader's MMA issuer waits for both CTAs
-        else ptx::mbar_arrive(&tmem_empty_bar[as]);
+      // accumulator stage drained: hand it back to the MMA issuer (the 16-bit epilogues did so after their last load)
+      if constexpr (!kOut16) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (TWO) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);  // the leader's MMA issuer waits for both CTAs
+          else ptx::mbar_arrive(&tmem_empty_bar[as]);
+        }
       }
     }
-    if constexpr (EPI == EPI_BIAS_RES_32) {
+    if constexpr (EPI == EPI_BIAS_RES_32 || kOut16) {
       if (lane == 0) ptx::bulk_wait_all();  // smem must outlive the last TMA stores
     }
   }
@@ -633,7 +644,20 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, co
   if (!out16 && ((p.N & 3) || (p.ldo & 3) || p.out32 == nullptr)) return cudaErrorInvalidValue;
   if (p.epilogue == EPI_PATCH_32 && (p.pos == nullptr || p.g2 <= 0)) return cudaErrorInvalidValue;
   if (p.epilogue == EPI_BIAS_RES_32 && (tmap_c == nullptr || (p.N & 31))) return cudaErrorInvalidValue;
-  const CUtensorMap& tc = tmap_c ? *tmap_c : tmap_a;  // unused by the other epilogues
+  CUtensorMap out_map;
+  if (out16 && tmap_c == nullptr) {  // the 16-bit epilogues store through TMA: 64-column x 32-row boxes over out16
+    if (reinterpret_cast<uintptr_t>(p.out16) & 15) return cudaErrorInvalidValue;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.N), static_cast<cuuint64_t>(p.M)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p.ldo) * 2};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    if (g_encode(&out_map, p.ab_format ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p.out16,
+                 gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    tmap_c = &out_map;
+  }
+  const CUtensorMap& tc = tmap_c ? *tmap_c : tmap_a;  // unused by the fp32 epilogues other than EPI_BIAS_RES_32
   const int m_blocks = (p.M + BM - 1) / BM;
   const int n_blocks = (p.N + block_n - 1) / block_n;
   if (pair) {  // tmap_w must have a 128-row box (half of the 256-wide W tile per CTA)

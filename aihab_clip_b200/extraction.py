@@ -118,9 +118,10 @@ class ShardedExtractor:
         starts = list(range(lo, hi, self.batch))
         host_out = None
         if self.copy_results_to_host:  # pinned result buffer is cached: cudaHostAlloc is slow and must not sit in the loop
-            if getattr(self, "_host_out", None) is None or tuple(self._host_out.shape) != (per, E + 1):
-                self._host_out = torch.empty(per, E + 1, dtype=torch.float32, pin_memory=True)
-            host_out = self._host_out
+            cached = getattr(self, "_host_out", None)
+            if cached is None or cached.shape[0] < per or cached.shape[1] != E + 1:  # grow-only cache
+                self._host_out = cached = torch.empty(per, E + 1, dtype=torch.float32, pin_memory=True)
+            host_out = cached[:per]
 
         def stage(i):
             b0 = starts[i]

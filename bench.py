@@ -280,7 +280,7 @@ def run_b200(args):
 
     ext = ShardedExtractor(model, head, batch_size=B, device=dev, rank=rank, world_size=world,
                            copy_results_to_host=True)
-    ext.run(source, 3 * B * world)  # warm-up of the copy pipeline
+    ext.run(source, n_local * world)  # warm-up of the copy pipeline at the timed size (pinned result buffer, allocator)
     ext.h2d_bytes = ext.d2h_bytes = 0
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
