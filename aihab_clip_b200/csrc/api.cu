@@ -86,18 +86,22 @@ int fail(const std::string& msg) {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-// attention kernel choice: 2 = persistent tcgen05 (L <= 224), 1 = tcgen05 (L <= 256), 0 = mma.sync (any L <= 908).
+// attention kernel choice: 3 = persistent flash tcgen05 (L > 224), 2 = persistent tcgen05 (64 < L <= 224),
+// 1 = tcgen05 (L <= 256), 0 = mma.sync (any L <= 908).
 // AIHAB_ATTN=legacy|tc|tcp caps the choice (A/B measurements); default picks the fastest supported kernel.
 int attention_kind(int L) {
-  int cap = 2;
+  int cap = 3;
   if (const char* e = getenv("AIHAB_ATTN")) {
     if (!strcmp(e, "legacy")) cap = 0;
     else if (!strcmp(e, "tc")) cap = 1;
+    else if (!strcmp(e, "tcp")) cap = 2;
   }
   if (cap >= 2 && aihab::attention_tcp_supported(L)) return 2;
+  if (cap >= 3 && aihab::attention_tcf_supported(L)) return 3;
   if (cap >= 1 && aihab::attention_tc_supported(L)) return 1;
   return 0;
 }
+int attention_key_box(int kind, int L) { return kind == 3 ? 32 : aihab::attention_tc_key_rows(L); }
 
 struct DeviceGuard {
   int prev = -1;
@@ -307,6 +311,10 @@ struct aihab_vit {
   CUtensorMap m_patches, m_y, m_h, m_x;  // m_x: fp32 residual stream, {32,32} boxes (EPI_BIAS_RES_32)
   CUtensorMap m_attn_q, m_attn_kv;       // qkv view [cap_rows, 3D] of `big` for the tcgen05 attention
   int attn_kind = 0;
+  // side stream for the few query rows the flash attention leaves to the SIMT row kernel (L = 257): it runs
+  // concurrently with the tensor-core kernel, fork / join through the two events
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t ws_bytes = 0;
   std::vector<void*> allocs;
 };
@@ -462,7 +470,21 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
     }
     {
       ProfScope ps(PC_ATTN, 4.0 * n * L * L * D, s);
-      if (h->attn_kind == 2)
+      if (h->attn_kind == 3) {
+        const int tail = aihab::attention_tcf_tail_rows(L);
+        if (tail && h->side) CK(cudaEventRecord(h->ev_fork, s));
+        CKL(aihab::launch_attention_tcf(h->m_attn_q, h->m_attn_kv, h->big, h->y, n, L, h->cfg.heads, h->bf16,
+                                        h->num_sms, s, next_dir(), /*run_tail=*/!(tail && h->side)));
+        if (tail && h->side) {
+          // fork: the leftover rows run beside the tensor-core kernel.  Launched AFTER it so that the persistent CTAs
+          // (one per SM) are resident first and the small row CTAs fill the remaining thread slots.
+          CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+          CKL(aihab::launch_attention_rows(h->big, h->y, n, L, h->cfg.heads, h->bf16, L - tail, h->side));
+          CK(cudaEventRecord(h->ev_join, h->side));
+        }
+        if (tail && h->side) CK(cudaStreamWaitEvent(s, h->ev_join, 0));
+      }
+      else if (h->attn_kind == 2)
         CKL(aihab::launch_attention_tcp(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, h->num_sms, s,
                                         next_dir()));
       else if (h->attn_kind == 1)
@@ -663,11 +685,19 @@ int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, in
     return bail(1);
   }
   h->attn_kind = attention_kind(L);
+  if (h->attn_kind == 3 && aihab::attention_tcf_tail_rows(L) > 0 && getenv("AIHAB_ATTN_SERIAL_TAIL") == nullptr) {
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      fail("aihab_vit_create: could not create the attention side stream");
+      return bail(1);
+    }
+  }
   if (h->attn_kind > 0) {
     const uint64_t pitch = static_cast<uint64_t>(3 * D) * 2;
     if (aihab::make_tmap_2d_16bit(&h->m_attn_q, h->big, h->cap_rows, 3 * D, pitch, 128, h->bf16) != cudaSuccess ||
-        aihab::make_tmap_2d_16bit(&h->m_attn_kv, h->big, h->cap_rows, 3 * D, pitch, aihab::attention_tc_key_rows(L),
-                                  h->bf16) != cudaSuccess) {
+        aihab::make_tmap_2d_16bit(&h->m_attn_kv, h->big, h->cap_rows, 3 * D, pitch,
+                                  attention_key_box(h->attn_kind, L), h->bf16) != cudaSuccess) {
       fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the attention views");
       return bail(1);
     }
@@ -681,6 +711,9 @@ void aihab_vit_destroy(aihab_vit* h) {
   if (h == nullptr) return;
   DeviceGuard guard(h->device);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
@@ -927,8 +960,10 @@ int aihab_attention(const void* qkv, void* out, int n, int L, int H, int dtype, 
     const uint64_t rows = static_cast<uint64_t>(n) * L, pitch = static_cast<uint64_t>(3 * H * 64) * 2;
     CK(aihab::gemm_init());
     CK(aihab::make_tmap_2d_16bit(&mq, qkv, rows, 3 * H * 64, pitch, 128, bf16));
-    CK(aihab::make_tmap_2d_16bit(&mkv, qkv, rows, 3 * H * 64, pitch, aihab::attention_tc_key_rows(L), bf16));
-    if (kind == 2)
+    CK(aihab::make_tmap_2d_16bit(&mkv, qkv, rows, 3 * H * 64, pitch, attention_key_box(kind, L), bf16));
+    if (kind == 3)
+      CKL(aihab::launch_attention_tcf(mq, mkv, qkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream)));
+    else if (kind == 2)
       CKL(aihab::launch_attention_tcp(mq, mkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream)));
     else
       CKL(aihab::launch_attention_tc(mq, mkv, out, n, L, H, bf16, static_cast<cudaStream_t>(stream)));

@@ -15,7 +15,7 @@ constexpr int HD = 64;  // head dim (width // 64 heads, clip/model.py:267)
 
 template <bool BF16>
 __global__ void __launch_bounds__(256, 2)
-attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int L, int H, int Lp) {
+attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int L, int H, int Lp, int q_tile0) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + static_cast<size_t>(Lp) * 128;
@@ -48,7 +48,7 @@ attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, i
   const uint32_t sK_u = ptx::smem_u32(sK), sV_u = ptx::smem_u32(sV);
   const int lm = lane >> 3, lr = lane & 7;  // ldmatrix: matrix id and row inside it
 
-  for (int qt = warp; qt < q_tiles; qt += nwarps) {
+  for (int qt = q_tile0 + warp; qt < q_tiles; qt += nwarps) {  // q_tile0 > 0: only the rows from 16 * q_tile0 on
     const int q0 = qt * 16;
     // Q fragments straight from global memory in the m16k16 A layout (4 k-steps x 4 regs)
     uint32_t qa[4][4];
@@ -166,6 +166,111 @@ attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, i
   }
 }
 
+// A few query rows per (image, head): one 8-warp CTA per row, no tensor cores.  Eight consecutive lanes share a key
+// (one 16-byte chunk = 8 head dims each), so a warp reads four complete 128-byte K (V) rows per load instruction and
+// every thread has several independent loads in flight.  Scores pass through smem (L <= 1024 floats); the partial
+// sum_k p_k V_k is folded over the four key slots of a warp with shuffles and over the warps through smem, all fp32.
+// Used for the <= 16 rows the 128-row tiles of the flash kernel leave over (L = 257: row 256).
+constexpr int ROWS_MAX_L = 1024;
+
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const float2 a = ptx::unpack2<BF16>(v.x), b = ptx::unpack2<BF16>(v.y), c = ptx::unpack2<BF16>(v.z),
+               d = ptx::unpack2<BF16>(v.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+attention_rows_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int L, int H, int q_row0, int n_rows) {
+  __shared__ float s_p[ROWS_MAX_L];
+  __shared__ float s_red[16];
+  __shared__ float s_o[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ks = lane >> 3, c = lane & 7;  // key slot of the warp, 16-byte chunk (head dims 8c .. 8c + 7)
+  const int r = blockIdx.x % n_rows;
+  const int u = blockIdx.x / n_rows;
+  const int h = u % H;
+  const int img = u / H;
+  const int D = H * HD;
+  const size_t ld = static_cast<size_t>(3) * D;
+  const uint16_t* base = qkv + static_cast<size_t>(img) * L * ld + h * HD + 8 * c;
+  const int qrow = q_row0 + r;
+  const float sl2 = 0.125f * 1.4426950408889634f;
+
+  float qf[8];
+  unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(qrow) * ld)), qf);
+  float m = -INFINITY;
+#pragma unroll 4
+  for (int kb = warp * 4; kb < L; kb += 32) {  // warp-uniform trip count
+    const int key = kb + ks;
+    const bool valid = key < L;
+    float kf[8];
+    unpack8<BF16>(valid ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(key) * ld + D))
+                        : make_uint4(0u, 0u, 0u, 0u), kf);
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc = fmaf(qf[e], kf[e], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (valid) {
+      acc *= sl2;
+      m = fmaxf(m, acc);
+      if (c == 0) s_p[key] = acc;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  m = s_red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
+
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  float l = 0.f;
+#pragma unroll 4
+  for (int kb = warp * 4; kb < L; kb += 32) {
+    const int key = kb + ks;
+    if (key < L) {
+      const float pk = exp2f(s_p[key] - m);
+      if (c == 0) l += pk;
+      float vf[8];
+      unpack8<BF16>(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(key) * ld + 2 * D)), vf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaf(pk, vf[e], o[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {  // fold the four key slots of the warp
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+  if (ks == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_o[warp][8 * c + e] = o[e];
+  }
+  if (lane == 0) s_red[8 + warp] = l;
+  __syncthreads();
+  if (warp == 0) {
+    float lt = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      lt += s_red[8 + w];
+      o0 += s_o[w][2 * lane];
+      o1 += s_o[w][2 * lane + 1];
+    }
+    const float inv = 1.0f / lt;
+    uint16_t* dst = out + (static_cast<size_t>(img) * L + qrow) * D + h * HD;
+    *reinterpret_cast<uint32_t*>(dst + 2 * lane) = ptx::pack2<BF16>(o0 * inv, o1 * inv);
+  }
+}
+
 int g_attn_max_smem[64] = {};  // per device: cudaFuncSetAttribute is a per-device setting
 
 }  // namespace
@@ -200,9 +305,37 @@ cudaError_t launch_attention(const void* qkv, void* out, int n_img, int L, int H
   const int nwarps = (q_tiles + rounds - 1) / rounds;
   dim3 grid(H, n_img);
   if (is_bf16)
-    attention_kernel<true><<<grid, nwarps * 32, smem, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), L, H, Lp);
+    attention_kernel<true><<<grid, nwarps * 32, smem, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), L, H, Lp, 0);
   else
-    attention_kernel<false><<<grid, nwarps * 32, smem, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), L, H, Lp);
+    attention_kernel<false><<<grid, nwarps * 32, smem, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), L, H, Lp, 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attention_rows(const void* qkv, void* out, int n_img, int L, int H, int is_bf16, int q_row0,
+                                  cudaStream_t stream) {
+  if (n_img <= 0 || q_row0 >= L) return cudaSuccess;
+  if (L <= 0 || H <= 0 || q_row0 < 0 || (q_row0 & 15)) return cudaErrorInvalidValue;
+  if (L - q_row0 <= 16 && L <= ROWS_MAX_L) {  // a handful of rows: one small CTA each, no smem staging
+    const int n_rows = L - q_row0;
+    const int grid = n_img * H * n_rows;
+    if (is_bf16)
+      attention_rows_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), L, H, q_row0, n_rows);
+    else
+      attention_rows_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), L, H, q_row0, n_rows);
+    return cudaGetLastError();
+  }
+  const int Lp = (L + 63) / 64 * 64;
+  const int smem = Lp * 256;
+  {
+    cudaError_t e = attention_init(L);
+    if (e != cudaSuccess) return e;
+  }
+  // all 8 warps stage K / V; only the first (L - q_row0 + 15) / 16 of them own a query tile
+  dim3 grid(H, n_img);
+  if (is_bf16)
+    attention_kernel<true><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), L, H, Lp, q_row0 >> 4);
+  else
+    attention_kernel<false><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), L, H, Lp, q_row0 >> 4);
   return cudaGetLastError();
 }
 

@@ -29,6 +29,9 @@ cudaError_t launch_im2col(const void* images, int in_dtype, int n, int R, int p,
 //   out : [N*L, D] 16-bit
 cudaError_t launch_attention(const void* qkv, void* out, int n_img, int L, int H, int is_bf16, cudaStream_t stream);
 cudaError_t attention_init(int max_L);
+// Same kernel restricted to the query rows >= q_row0 (q_row0 % 16 == 0): the tail of launch_attention_tcf.
+cudaError_t launch_attention_rows(const void* qkv, void* out, int n_img, int L, int H, int is_bf16, int q_row0,
+                                  cudaStream_t stream);
 
 // tcgen05 / TMEM variant for 64 < L <= 256 (ViT-B/16's 197 tokens): S and O live in TMEM, softmax reads S with
 // tcgen05.ld.  tmap_q: make_tmap_2d_16bit over qkv [n*L, 3D] with a 128-row box; tmap_kv: same matrix with an
@@ -43,6 +46,17 @@ cudaError_t launch_attention_tc(const CUtensorMap& tmap_q, const CUtensorMap& tm
 bool attention_tcp_supported(int L);
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
                                  int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse = 0);
+
+// Persistent flash-style variant for long sequences (128 < L <= 1024; ViT-L/14: 257, ViT-L/14@336px: 577): keys in
+// blocks of <= 160 with an online softmax, O rescaled in TMEM only when the running max moves by more than 2^8.
+// tmap_q as above; tmap_kv32: the same matrix with a 32-row box.  A tail of <= 16 query rows beyond the last full
+// 128-row tile is computed by launch_attention_rows (needs the raw qkv pointer) after the flash kernel on the same
+// stream, or by the caller on another stream when run_tail is false (rows >= L - attention_tcf_tail_rows(L)).
+bool attention_tcf_supported(int L);
+int attention_tcf_tail_rows(int L);
+cudaError_t launch_attention_tcf(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv32, const void* qkv, void* out,
+                                 int n_img, int L, int H, int is_bf16, int num_sms, cudaStream_t stream,
+                                 int reverse = 0, bool run_tail = true);
 
 // fp32 -> 16-bit cast of a weight matrix [rows, cols] into [rows, cols_pad] (zero padded columns).
 cudaError_t launch_cast_pad(const float* src, int rows, int cols, void* dst, int cols_pad, int out_bf16,

@@ -108,7 +108,8 @@ def test_layernorm(cuda_device, D, out_dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("L,H,n", [(50, 12, 3), (197, 12, 2), (257, 16, 2), (577, 16, 1), (17, 2, 4), (64, 1, 1),
-                                   (256, 4, 2), (100, 2, 3), (129, 2, 2), (65, 1, 5), (197, 12, 9)])
+                                   (256, 4, 2), (100, 2, 3), (129, 2, 2), (65, 1, 5), (197, 12, 9), (225, 2, 3),
+                                   (272, 3, 5), (273, 2, 2), (384, 2, 2), (600, 1, 2), (1024, 1, 1), (257, 16, 40)])
 def test_attention(cuda_device, dtype, L, H, n):
     _lib, ops = _ops()
     rng = np.random.default_rng(L + H)
@@ -122,6 +123,28 @@ def test_attention(cuda_device, dtype, L, H, n):
     # P is rounded to 16 bits before PV and the output is 16-bit: error ~ eps * |v|
     eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
     np.testing.assert_allclose(out, ref, atol=eps * 3, rtol=eps * 2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("L,H,n", [(257, 2, 3), (577, 2, 2), (300, 1, 4)])
+def test_attention_online_rescale(cuda_device, dtype, L, H, n):
+    """Peaky scores whose maximum grows along the key axis: every key block of the flash kernel raises the running
+    row maximum by much more than 2^8, so the O rescale in TMEM runs at every block (clip/model.py:179-181)."""
+    _lib, ops = _ops()
+    rng = np.random.default_rng(7 * L + H)
+    D = H * 64
+    q = rng.standard_normal((n, L, H, 64)) * 2.0
+    k = rng.standard_normal((n, L, H, 64)) * (0.5 + 3.0 * np.arange(L)[None, :, None, None] / L)
+    v = rng.standard_normal((n, L, H, 64))
+    qkv = torch.from_numpy(np.concatenate([q, k, v], axis=2).reshape(n * L, 3 * D)).to(dtype)
+    out = ops.attention(qkv.to(cuda_device), n, L, H).float().cpu().numpy()
+    qd, kd, vd = (t.reshape(n, L, H, 64).transpose(0, 2, 1, 3) for t in np.split(qkv.double().numpy(), 3, axis=-1))
+    s_ = qd @ kd.transpose(0, 1, 3, 2) / 8.0
+    p_ = np.exp(s_ - s_.max(-1, keepdims=True))
+    ref = ((p_ / p_.sum(-1, keepdims=True)) @ vd).transpose(0, 2, 1, 3).reshape(n * L, D)
+    assert np.isfinite(out).all()
+    eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    np.testing.assert_allclose(out, ref, atol=eps * 4, rtol=eps * 3)
 
 
 def test_preprocess_bit_exact(cuda_device, gold, meta):
