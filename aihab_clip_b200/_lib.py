@@ -44,6 +44,7 @@ SIGNATURES = {
     "aihab_vit_create": (C.c_int, [C.POINTER(VitConfig), C.POINTER(VitWeights), C.c_int, C.POINTER(C.c_void_p)]),
     "aihab_vit_destroy": (None, [C.c_void_p]),
     "aihab_vit_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "aihab_preferred_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "aihab_vit_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "aihab_vit_encode_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "aihab_preprocess_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

@@ -164,6 +164,13 @@ class VisionTransformer(nn.Module):
             self._engine_key = key
         return self._engine
 
+    def preferred_batch(self, device: torch.device, max_batch: int | None = None) -> int:
+        """Images per encode call (<= max_batch) whose GEMMs fill the device's SMs with whole waves of tiles; the
+        batch size to use for extraction loops (the reference uses a fixed 16, methods/utils.py:142-173)."""
+        tokens = (self.input_resolution // self.conv1.kernel_size[0]) ** 2 + 1
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        return int(_lib.load().aihab_preferred_batch(tokens, self.conv1.out_channels, int(max_batch or self.max_batch), idx))
+
     def _check_device(self, x: torch.Tensor):
         if not x.is_cuda:
             raise RuntimeError("aihab_clip_b200 image tower runs on a B200 CUDA device only (no CPU fallback); "

@@ -719,6 +719,38 @@ void aihab_vit_destroy(aihab_vit* h) {
 
 size_t aihab_vit_workspace_bytes(const aihab_vit* h) { return h ? h->ws_bytes : 0; }
 
+int aihab_preferred_batch(int tokens, int width, int max_batch, int device) {
+  if (tokens <= 0 || width <= 0 || max_batch <= 0) return max_batch > 0 ? max_batch : 1;
+  const int sms = sm_count(device);
+  const long shapes[4][2] = {{3L * width, width}, {width, width}, {4L * width, width}, {width, 4L * width}};
+  int best = max_batch;
+  double best_eff = -1.0;
+  for (int b = std::max(1, max_batch / 2); b <= max_batch; ++b) {
+    const long M = static_cast<long>(b) * tokens;
+    double flops = 0.0, time = 0.0;  // time in per-SM tile MACs summed over whole waves
+    for (const auto& nk : shapes) {
+      const int N = static_cast<int>(nk[0]);
+      const long K = nk[1];
+      const int bn = aihab::gemm_block_n(static_cast<int>(M), N, sms);
+      const bool pair = aihab::gemm_use_pair(static_cast<int>(M), N, sms);
+      const long m_blocks = (M + 127) / 128, n_blocks = (N + bn - 1) / bn;
+      const long tiles = (pair ? (m_blocks + 1) / 2 : m_blocks) * n_blocks;
+      const long units = pair ? sms / 2 : sms;
+      const long waves = (tiles + units - 1) / units;
+      // measured: a CTA pair moves half the W bytes per SM, a 128-wide tile twice the A bytes per FLOP
+      const double tile_penalty = pair ? 1.0 : (bn == 256 ? 1.05 : 1.15);
+      time += static_cast<double>(waves) * 128.0 * bn * K * tile_penalty;
+      flops += static_cast<double>(M) * N * K;
+    }
+    const double eff = flops / (time * sms);
+    if (eff >= best_eff) {  // ties go to the larger batch
+      best_eff = eff;
+      best = b;
+    }
+  }
+  return best;
+}
+
 int aihab_vit_encode(aihab_vit* h, const void* images, int in_dtype, int n, void* feats_out, int out_dtype,
                      void* stream) {
   if (h == nullptr) return fail("aihab_vit_encode: null handle");

@@ -83,6 +83,7 @@ attention_tcf_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     h = u - img * H;
   };
 
+  ptx::griddep_launch();
   if (warp == 0) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmap_q);
@@ -100,6 +101,7 @@ attention_tcf_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  ptx::griddep_wait();  // qkv comes from the previous kernel of the stream
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -355,8 +357,7 @@ cudaError_t launch_f(const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* ou
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  attention_tcf_kernel<BF16><<<grid, F_THREADS, F_SMEM, stream>>>(tq, tkv, out, p);
-  return cudaGetLastError();
+  return launch_kernel(attention_tcf_kernel<BF16>, grid, F_THREADS, F_SMEM, stream, 1, true, tq, tkv, out, p);
 }
 
 }  // namespace

@@ -131,6 +131,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     h = u - img * H;
   };
 
+  ptx::griddep_launch();
   if (warp == 0) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmap_q);
@@ -154,6 +155,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  ptx::griddep_wait();  // qkv comes from the previous kernel of the stream
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -288,8 +290,8 @@ cudaError_t launch_nc(const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* o
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  attention_tcp_kernel<BF16, NC><<<grid, P_THREADS, P_SMEM, stream>>>(tq, tkv, out, L, H, Lk, nq, total, reverse);
-  return cudaGetLastError();
+  return launch_kernel(attention_tcp_kernel<BF16, NC>, grid, P_THREADS, P_SMEM, stream, 1, true, tq, tkv, out, L, H, Lk, nq,
+                       total, reverse);
 }
 
 template <bool BF16>

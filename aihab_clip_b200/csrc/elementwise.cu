@@ -1,5 +1,7 @@
 // HBM-bound kernels of the hot path: LayerNorm, im2col, weight cast.  128-bit loads/stores, one warp per row.
 #include "kernels.cuh"
+
+#include <cstdlib>
 #include "ptx.cuh"
 
 namespace aihab {
@@ -20,6 +22,8 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, float* out32, void* out16,
                                                         int out_bf16, int rows) {
   constexpr int D = VPL * 128;
+  ptx::griddep_launch();
+  ptx::griddep_wait();  // x comes from the previous kernel of the stream
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -139,16 +143,25 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, int rows, int col
 
 }  // namespace
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("AIHAB_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 cudaError_t launch_layernorm(const float* x, size_t ldx, const float* cls0, int L, const float* gamma,
                              const float* beta, float* out32, void* out16, int out_bf16, int rows, int D,
                              cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   if (D % 128 != 0 || D > 2048 || (ldx & 3) != 0) return cudaErrorInvalidValue;
   const int grid = (rows + 3) / 4;
+  cudaError_t e = cudaSuccess;
 #define AIHAB_LN(V)                                                                                            \
   case V:                                                                                                      \
-    layernorm_kernel<V><<<grid, 128, 0, stream>>>(x, ldx, cls0, L > 0 ? L : 1, gamma, beta, out32, out16,       \
-                                                  out_bf16, rows);                                             \
+    e = launch_kernel(layernorm_kernel<V>, grid, 128, 0, stream, 1, true, x, ldx, cls0, L > 0 ? L : 1, gamma, beta, \
+                      out32, out16, out_bf16, rows);                                                             \
     break;
   switch (D / 128) {
     AIHAB_LN(1) AIHAB_LN(2) AIHAB_LN(3) AIHAB_LN(4) AIHAB_LN(5) AIHAB_LN(6) AIHAB_LN(7) AIHAB_LN(8)
@@ -156,7 +169,7 @@ cudaError_t launch_layernorm(const float* x, size_t ldx, const float* cls0, int 
     default: return cudaErrorInvalidValue;
   }
 #undef AIHAB_LN
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t launch_im2col(const void* images, int in_dtype, int n, int R, int p, int Kpad, void* out, int out_bf16,

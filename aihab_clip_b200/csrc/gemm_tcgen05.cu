@@ -1,5 +1,6 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a.  See gemm_tcgen05.cuh for the contract.
 #include "gemm_tcgen05.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
 
 #include <cudaTypedefs.h>
@@ -108,6 +109,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     return TWO ? 2 * mb + cta_rank : mb;
   };
 
+  ptx::griddep_launch();  // the next kernel of the stream may be scheduled as soon as SM resources free up
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_w);
@@ -142,6 +144,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::griddep_wait();  // everything above overlaps the tail of the previous kernel; global memory only from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -516,24 +519,12 @@ template <int BN, int EPI>
 cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const GemmParams& p,
                        int grid, bool pair, cudaStream_t stream) {
   if constexpr (BN == 256) {
-    if (pair) {  // CTA pairs: cluster of 2, grid = 2 x #pairs
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(num_threads(EPI));
-      cfg.dynamicSmemBytes = SmemLayout<256, EPI, true>::kDynamic;
-      cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      return cudaLaunchKernelEx(&cfg, gemm_kernel<256, EPI, true>, ta, tw, tc, p);
-    }
+    if (pair)  // CTA pairs: cluster of 2, grid = 2 x #pairs
+      return launch_kernel(gemm_kernel<256, EPI, true>, grid, num_threads(EPI), SmemLayout<256, EPI, true>::kDynamic,
+                           stream, 2, true, ta, tw, tc, p);
   }
-  gemm_kernel<BN, EPI, false><<<grid, num_threads(EPI), SmemLayout<BN, EPI, false>::kDynamic, stream>>>(ta, tw, tc, p);
-  return cudaGetLastError();
+  return launch_kernel(gemm_kernel<BN, EPI, false>, grid, num_threads(EPI), SmemLayout<BN, EPI, false>::kDynamic, stream,
+                       1, true, ta, tw, tc, p);
 }
 
 template <int BN>

@@ -58,6 +58,36 @@ cudaError_t launch_attention_tcf(const CUtensorMap& tmap_q, const CUtensorMap& t
                                  int n_img, int L, int H, int is_bf16, int num_sms, cudaStream_t stream,
                                  int reverse = 0, bool run_tail = true);
 
+// Launch helper: cudaLaunchKernelEx with an optional cluster dimension and programmatic dependent launch (the kernel
+// must call ptx::griddep_wait() before its first global-memory access).  AIHAB_PDL=0 disables the latter.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, int cluster,
+                          bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl && pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // fp32 -> 16-bit cast of a weight matrix [rows, cols] into [rows, cols_pad] (zero padded columns).
 cudaError_t launch_cast_pad(const float* src, int rows, int cols, void* dst, int cols_pad, int out_bf16,
                             cudaStream_t stream);

@@ -185,6 +185,13 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// griddep_launch: lets the next kernel of the stream (launched with programmatic stream serialization) be scheduled
+// while this grid still runs; griddep_wait: blocks until the previous grid has completed and its memory is visible.
+// Every global-memory access of a kernel launched that way must come after griddep_wait.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 // A CTA pair is a cluster of two CTAs on one TPC.  The even CTA (cluster rank 0) is the leader: it issues the MMAs
 // for both, and barriers that both CTAs signal live in ITS shared memory.  Clearing bit 24 of a shared::cta address

@@ -105,6 +105,10 @@ AIHAB_API int aihab_profile_read(int cls, double* ms, uint64_t* launches, double
 AIHAB_API int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, int device, aihab_vit** out);
 AIHAB_API void aihab_vit_destroy(aihab_vit* h);
 AIHAB_API size_t aihab_vit_workspace_bytes(const aihab_vit* h);
+/* Images per call (<= max_batch, >= max_batch / 2) whose transformer GEMMs fill `device`'s SMs with whole waves of
+ * 256 x 256 tiles: the batch size to feed aihab_vit_encode* / the extraction loop (methods/utils.py:142-173 uses a
+ * fixed 16).  tokens = (image_size / patch_size)^2 + 1, width = transformer width.  No handle needed. */
+AIHAB_API int aihab_preferred_batch(int tokens, int width, int max_batch, int device);
 
 /* Replaces CLIP.encode_image / VisionTransformer.forward (clip/model.py:216-235, 335-336).
  *   images   : [n, 3, R, R] NCHW, element type in_dtype, already normalised (output of the preprocess)

@@ -174,3 +174,16 @@ def test_weights_generator_geometry():
     assert sd["visual.conv1.weight"].shape == (256, 3, 14, 14)
     assert all(k.startswith("visual.") for k in sd)
     assert torch.equal(sd["visual.proj"], sd["visual.proj"].half().float())
+
+
+def test_preferred_batch_fills_whole_waves():
+    """aihab_preferred_batch is host arithmetic (no kernel launch): the chosen batch keeps every transformer GEMM
+    within a few percent of whole waves of 256-row tile pairs on 148 SMs, and never exceeds the bound."""
+    from aihab_clip_b200 import _lib
+    lib = _lib.load()
+    for tokens, width, bound in [(50, 768, 1024), (197, 768, 256), (257, 1024, 128), (577, 1024, 64), (197, 768, 7)]:
+        b = lib.aihab_preferred_batch(tokens, width, bound, 0)
+        assert max(1, bound // 2) <= b <= bound
+    b = lib.aihab_preferred_batch(50, 768, 1024, 0)
+    pair_tiles = -(-b * 50 // 256)
+    assert pair_tiles % 74 == 0  # ViT-B/32: 757 images = 148 tile pairs = 2 per SM pair

@@ -40,11 +40,13 @@ def main():
     dev = torch.device("cuda:0")
     peaks = measured_peaks()
     rows = []
-    cases = [("ViT-B/32", 512, 20), ("ViT-B/16", 128, 20), ("ViT-L/14", 128, 20), ("ViT-L/14@336px", 64, 20)]
-    for arch, batch, classes in cases:
+    # (arch, upper bound of the per-step batch, classes): the step batch is the library's preferred batch under the bound
+    cases = [("ViT-B/32", 1024, 20), ("ViT-B/16", 256, 20), ("ViT-L/14", 128, 20), ("ViT-L/14@336px", 48, 20)]
+    for arch, max_batch, classes in cases:
         geom = GEOMETRIES[arch]
         model = build_model(make_state_dict(geom, 0, with_text=False if False else True)).to(dev).float()
         model.visual.compute_dtype = args.dtype
+        batch = model.visual.preferred_batch(dev, max_batch)
         model.visual.max_batch = batch
         tw = torch.nn.functional.normalize(torch.randn(classes, geom.embed_dim, device=dev), dim=1).t().contiguous()
         head = ZeroShotHead.from_model(model, tw, dev)
