@@ -1,12 +1,17 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel:  python tools/launch_summary.py csv [out]"""
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel:
+    python tools/launch_summary.py csv [out] [--all]
+By default only this library's kernels (namespace aihab::) are kept: the list also holds the one-off PyTorch launches
+of the benchmark set-up (text tower for the class head, weight casts, synthetic-input generators)."""
 import collections, csv, re, sys
+keep_all = "--all" in sys.argv
+sys.argv = [a for a in sys.argv if a != "--all"]
 rows = list(csv.reader(open(sys.argv[1])))
 start = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 hdr = rows[start]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 agg = collections.OrderedDict()
 for r in rows[start + 1:]:
-    if len(r) <= vi:
+    if len(r) <= vi or (not keep_all and "aihab::" not in r[ki]):
         continue
     name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("aihab::<unnamed>::", "")[:64]
     v = float(r[vi].replace(",", ""))
