@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 attention_tcf_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                      uint16_t* __restrict__ out, const FlashParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024 B aligned, still a __shared__ pointer
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* bar_q = bars + 0;        // [2] Q tile of an item landed
   uint64_t* bar_qfree = bars + 2;    // [2] every S MMA of the item has retired

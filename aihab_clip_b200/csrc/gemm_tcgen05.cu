@@ -80,7 +80,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr bool kOut16 = (EPI == EPI_BIAS_16 || EPI == EPI_BIAS_GELU_16 || kLn);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024 B aligned, still a __shared__ pointer
   uint8_t* sA = smem + L::kOffA;
   uint8_t* sB = smem + L::kOffB;
   uint8_t* sStaging = smem + L::kOffStaging;
