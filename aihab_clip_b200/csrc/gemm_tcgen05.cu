@@ -249,6 +249,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int i = 0; i < RS - 1; ++i) res_prefetch(i);
       }
     }
+    // per-column vectors of a tile (bias; s_n or gamma) are fetched ONE TILE AHEAD into registers and parked in smem
+    // at the start of the tile, so their global-load latency never sits in front of an epilogue
+    constexpr int NV = (BN + kEpiThreads - 1) / kEpiThreads;
+    const bool ln_prod = (EPI == EPI_BIAS_RES_32) && p.ln_gamma != nullptr;
+    const float* aux = kLn ? p.ln_s : p.ln_gamma;
+    float nxt_b[NV], nxt_x[NV];
+    auto fetch_cols = [&](int tile) {
+      const int nbase = (tile % n_blocks) * BN;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int i = et + v * kEpiThreads;
+        const int n = nbase + i;
+        const bool ok = tile < num_tiles && i < BN && n < p.N;
+        nxt_b[v] = (ok && p.bias != nullptr) ? __ldg(p.bias + n) : 0.0f;
+        nxt_x[v] = (ok && (kLn || ln_prod)) ? __ldg(aux + n) : 0.0f;
+      }
+    };
+    if constexpr (EPI != EPI_PATCH_32) fetch_cols(unit);
     int it = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int m_blk = tile_m(tile);
@@ -260,15 +278,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
       float* sb = sBias + as * BN;
       float* sx = sBias + (2 + as) * BN;  // s_n (LayerNorm consumer) or gamma (LayerNorm producer)
-      const bool ln_prod = (EPI == EPI_BIAS_RES_32) && p.ln_gamma != nullptr;
       if constexpr (EPI != EPI_PATCH_32) {
-        const float* aux = kLn ? p.ln_s : p.ln_gamma;
-        for (int i = et; i < BN; i += kEpiThreads) {
-          const int n = n0 + i;
-          sb[i] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.0f;
-          if (kLn || ln_prod) sx[i] = n < p.N ? __ldg(aux + n) : 0.0f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int i = et + v * kEpiThreads;
+          if (i < BN) {
+            sb[i] = nxt_b[v];
+            if (kLn || ln_prod) sx[i] = nxt_x[v];
+          }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        fetch_cols(tile + num_units);  // in flight during this tile's epilogue
       }
       // LayerNorm consumer: statistics of this thread's row from the producer's per-tile partial sums
       float ln_r = 1.0f, ln_nrm = 0.0f;
@@ -367,24 +387,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           ptx::mbar_wait(&my_full[slot], (q / RS) & 1);
           ptx::tmem_ld_wait();
           uint8_t* box = my_ring + slot * RES_BOX;
+          // all loads of the box first, then the arithmetic, then all stores: the shared-memory latency is paid once
+          float4 xv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) xv[u] = *reinterpret_cast<const float4*>(box + lane * 128 + ((u ^ (lane & 7)) << 4));
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            float4* px = reinterpret_cast<float4*>(box + lane * 128 + ((u ^ (lane & 7)) << 4));
-            float4 v = *px;
-            v.x += __uint_as_float(r[4 * u]) + sb[c * 32 + 4 * u];
-            v.y += __uint_as_float(r[4 * u + 1]) + sb[c * 32 + 4 * u + 1];
-            v.z += __uint_as_float(r[4 * u + 2]) + sb[c * 32 + 4 * u + 2];
-            v.w += __uint_as_float(r[4 * u + 3]) + sb[c * 32 + 4 * u + 3];
-            *px = v;
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + 4 * u);
+            float4 v = xv[u];
+            v.x += __uint_as_float(r[4 * u]) + b4.x;
+            v.y += __uint_as_float(r[4 * u + 1]) + b4.y;
+            v.z += __uint_as_float(r[4 * u + 2]) + b4.z;
+            v.w += __uint_as_float(r[4 * u + 3]) + b4.w;
+            xv[u] = v;
             if (ln_prod) {  // reuse r[] for the packed gamma * x_new row segment
               ln_s1 += (v.x + v.y) + (v.z + v.w);
               ln_s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ln_s2))));
-              const float g0 = sx[c * 32 + 4 * u], g1 = sx[c * 32 + 4 * u + 1], g2 = sx[c * 32 + 4 * u + 2],
-                          g3 = sx[c * 32 + 4 * u + 3];
-              r[2 * u] = bf16 ? ptx::pack2<true>(g0 * v.x, g1 * v.y) : ptx::pack2<false>(g0 * v.x, g1 * v.y);
-              r[2 * u + 1] = bf16 ? ptx::pack2<true>(g2 * v.z, g3 * v.w) : ptx::pack2<false>(g2 * v.z, g3 * v.w);
+              const float4 g4 = *reinterpret_cast<const float4*>(sx + c * 32 + 4 * u);
+              r[2 * u] = bf16 ? ptx::pack2<true>(g4.x * v.x, g4.y * v.y) : ptx::pack2<false>(g4.x * v.x, g4.y * v.y);
+              r[2 * u + 1] = bf16 ? ptx::pack2<true>(g4.z * v.z, g4.w * v.w) : ptx::pack2<false>(g4.z * v.z, g4.w * v.w);
             }
           }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(box + lane * 128 + ((u ^ (lane & 7)) << 4)) = xv[u];
           if (ln_prod) {  // gamma * x_new: transpose through smem so each store covers 8 complete 64 B row segments
             uint8_t* ast = sStaging + 4 * RS * RES_BOX + ew * 2048;
 #pragma unroll
