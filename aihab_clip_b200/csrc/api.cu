@@ -933,6 +933,21 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
   return 0;
 }
 
+int aihab_l2_metrics(const float* logits_l3, int n, int C3, const int32_t* l3_to_l2, int C2, int reduce, int k,
+                     float* logits_l2_out, int64_t* topk_idx, float* topk_val, int64_t* top3_idx, float* top3_prob,
+                     void* stream) {
+  if (logits_l3 == nullptr || l3_to_l2 == nullptr || n < 0) return fail("aihab_l2_metrics: bad argument");
+  if (C3 <= 0 || C3 > 1024 || C2 <= 0 || C2 > 256) return fail("aihab_l2_metrics: needs 1 <= C3 <= 1024 and 1 <= C2 <= 256");
+  if (reduce < 0 || reduce > 2) return fail("aihab_l2_metrics: reduce must be 0 (sum), 1 (mean) or 2 (logsumexp)");
+  if (k < 0 || k > C2 || (k > 0 && topk_idx == nullptr)) return fail("aihab_l2_metrics: 0 <= k <= C2 and topk_idx for k > 0");
+  if (n == 0) return 0;
+  DeviceGuard guard(device_of(logits_l3));
+  ProfScope ps(PC_SCORE, static_cast<double>(n) * C3 * 2.0, static_cast<cudaStream_t>(stream));
+  CKL(aihab::launch_l2_metrics(logits_l3, n, C3, reinterpret_cast<const int*>(l3_to_l2), C2, reduce, k, logits_l2_out,
+                               topk_idx, topk_val, top3_idx, top3_prob, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype, int epilogue, const float* bias,
                  void* out16, float* out32, int ldo, const float* pos, int g2, float scale, void* stream) {
   if (A == nullptr || W == nullptr || M <= 0 || N <= 0 || K <= 0 || (K & 7)) return fail("aihab_gemm16: bad argument (K % 8 == 0)");

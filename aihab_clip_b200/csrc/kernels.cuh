@@ -108,6 +108,13 @@ cudaError_t launch_score_fused(const float* feats, int n, int D, const float* pr
                                float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx,
                                float* topk_val, cudaStream_t stream);
 
+// L3 -> L2 aggregation (reduce: 0 sum, 1 mean, 2 logsumexp, accumulated in L3-id order) + top-k over the L2 logits +
+// top-3 / softmax probabilities over the L3 logits, one launch (aihab_utils/evaluation.py:92-142, 186-221, 261-273).
+// l3_to_l2: device int32 [C3]; C3 <= 1024, C2 <= 256; every output pointer may be null (topk_idx only if k == 0).
+cudaError_t launch_l2_metrics(const float* logits_l3, int n, int C3, const int* l3_to_l2, int C2, int reduce, int k,
+                              float* logits_l2_out, int64_t* topk_idx, float* topk_val, int64_t* top3_idx,
+                              float* top3_prob, cudaStream_t stream);
+
 // tensor-core scoring helpers (aihab_score16): 16-bit transpose, fp16 hi/lo splits of the text weights and of the
 // normalised embedding (A' = e_hi | e_hi | e_lo against W' = w_hi | w_lo | w_hi reproduces the fp32 product to ~2^-21)
 cudaError_t launch_transpose16(const void* src, void* dst, int R, int Cc, cudaStream_t stream);

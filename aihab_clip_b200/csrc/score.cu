@@ -332,6 +332,186 @@ __global__ void __launch_bounds__(128) l2norm_split_kernel(const float* __restri
   }
 }
 
+// ---- L3 -> L2 aggregation + metrics epilogue (aihab_utils/evaluation.py:92-142, 186-221, 261-273), one launch.
+// One warp per row: the L3 logits row is staged in smem; lane g accumulates L2 group g over the L3 ids IN ID ORDER
+// (the reference's `for l3_id, l2_id in enumerate(...)` loop, so sum / mean are bit-identical to it);
+// then top-k over the L2 logits, and top-3 + softmax probabilities over the L3 logits.
+constexpr int L2M_MAX_C3 = 1024;
+constexpr int L2M_MAX_C2 = 256;
+
+__device__ __forceinline__ float logaddexp_ref(float a, float b) {
+  // torch.logaddexp: equal infinities return themselves, otherwise max + log1p(exp(-|a - b|))
+  if (isinf(a) && a == b) return a;
+  return fmaxf(a, b) + log1pf(expf(-fabsf(a - b)));
+}
+
+// warp top-k of src[0..cols) in (value desc, index asc) order; lane 0 writes idx / val / prob (prob = exp(v - m) * inv)
+__device__ __forceinline__ void warp_topk(const float* src, int cols, int k, int lane, int64_t* idx, float* val,
+                                          float* prob, float m, float inv) {
+  float last_v = INFINITY;
+  int last_i = -1;
+  for (int j = 0; j < k; ++j) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < cols; c += 32) {
+      const float v = src[c];
+      if (precedes(last_v, last_i, v, c) && precedes(v, c, bv, bi)) {
+        bv = v;
+        bi = c;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (precedes(ov, oi, bv, bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      if (idx != nullptr) idx[j] = bi;
+      if (val != nullptr) val[j] = bv;
+      if (prob != nullptr) prob[j] = expf(bv - m) * inv;
+    }
+    last_v = bv;
+    last_i = bi;
+  }
+}
+
+__global__ void __launch_bounds__(128) l2_metrics_kernel(const float* __restrict__ logits_l3, int n, int C3,
+                                                         const int* __restrict__ l3_to_l2, int C2, int reduce, int k,
+                                                         float* __restrict__ logits_l2_out,
+                                                         int64_t* __restrict__ topk_idx, float* __restrict__ topk_val,
+                                                         int64_t* __restrict__ top3_idx, float* __restrict__ top3_prob) {
+  extern __shared__ float l2m_smem[];
+  int* s_map = reinterpret_cast<int*>(l2m_smem);  // [C3]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_row = l2m_smem + C3 + warp * (C3 + C2);  // [C3] L3 logits, then [C2] L2 logits
+  float* s_l2 = s_row + C3;
+  for (int i = threadIdx.x; i < C3; i += blockDim.x) s_map[i] = l3_to_l2[i];
+  const int row = blockIdx.x * 4 + warp;
+  if (row < n) {
+    const float* src = logits_l3 + static_cast<size_t>(row) * C3;
+    for (int c = lane; c < C3; c += 32) s_row[c] = src[c];
+  }
+  __syncthreads();
+  if (row >= n) return;
+  for (int g = lane; g < C2; g += 32) {
+    float acc = reduce == 2 ? -INFINITY : 0.0f;
+    float cnt = 0.0f;
+    for (int c = 0; c < C3; ++c) {
+      if (s_map[c] == g) {
+        acc = reduce == 2 ? logaddexp_ref(acc, s_row[c]) : acc + s_row[c];
+        cnt += 1.0f;
+      }
+    }
+    if (reduce == 1) acc = acc / fmaxf(cnt, 1.0f);
+    s_l2[g] = acc;
+    if (logits_l2_out != nullptr) logits_l2_out[static_cast<size_t>(row) * C2 + g] = acc;
+  }
+  __syncwarp();
+  if (k > 0)
+    warp_topk(s_l2, C2, k, lane, topk_idx + static_cast<size_t>(row) * k,
+              topk_val != nullptr ? topk_val + static_cast<size_t>(row) * k : nullptr, nullptr, 0.f, 0.f);
+  if (top3_idx != nullptr || top3_prob != nullptr) {
+    float m = -INFINITY;
+    for (int c = lane; c < C3; c += 32) m = fmaxf(m, s_row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int c = lane; c < C3; c += 32) sum += expf(s_row[c] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const int k3 = C3 < 3 ? C3 : 3;
+    warp_topk(s_row, C3, k3, lane, top3_idx != nullptr ? top3_idx + static_cast<size_t>(row) * 3 : nullptr, nullptr,
+              top3_prob != nullptr ? top3_prob + static_cast<size_t>(row) * 3 : nullptr, m, 1.0f / sum);
+  }
+}
+
+// Thread-per-row variant for small class counts (the shipped 20 -> 11 map): 128 rows per CTA are staged through smem
+// with coalesced global reads / writes (odd row strides: conflict-free both ways), every thread walks its own row.
+// Same accumulation order as above (sum / mean bit-identical to the reference loop).
+__device__ __forceinline__ void thread_topk(const float* src, int cols, int k, int64_t* idx, float* val, float* prob,
+                                            float m, float inv) {
+  float last_v = INFINITY;
+  int last_i = -1;
+  for (int j = 0; j < k; ++j) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = 0; c < cols; ++c) {
+      const float v = src[c];
+      if (precedes(last_v, last_i, v, c) && precedes(v, c, bv, bi)) {
+        bv = v;
+        bi = c;
+      }
+    }
+    if (idx != nullptr) idx[j] = bi;
+    if (val != nullptr) val[j] = bv;
+    if (prob != nullptr) prob[j] = expf(bv - m) * inv;
+    last_v = bv;
+    last_i = bi;
+  }
+}
+
+__global__ void __launch_bounds__(128) l2_metrics_small_kernel(const float* __restrict__ logits_l3, int n, int C3,
+                                                               const int* __restrict__ l3_to_l2, int C2, int reduce,
+                                                               int k, float* __restrict__ logits_l2_out,
+                                                               int64_t* __restrict__ topk_idx,
+                                                               float* __restrict__ topk_val,
+                                                               int64_t* __restrict__ top3_idx,
+                                                               float* __restrict__ top3_prob) {
+  extern __shared__ float l2m_smem[];
+  const int st3 = C3 | 1, st2 = C2 | 1;
+  float* s_x = l2m_smem;               // [128][st3]
+  float* s_l2 = s_x + 128 * st3;       // [128][st2]
+  int* s_map = reinterpret_cast<int*>(s_l2 + 128 * st2);  // [C3]
+  float* s_cnt = reinterpret_cast<float*>(s_map + C3);    // [C2]
+  const int t = threadIdx.x;
+  const long row0 = static_cast<long>(blockIdx.x) * 128;
+  const int rows = static_cast<int>(min(static_cast<long>(128), n - row0));
+  for (int i = t; i < C3; i += 128) s_map[i] = l3_to_l2[i];
+  for (int i = t; i < C2; i += 128) s_cnt[i] = 0.f;
+  const float* src = logits_l3 + row0 * C3;
+  for (int e = t; e < rows * C3; e += 128) {
+    const int r = e / C3;
+    s_x[r * st3 + (e - r * C3)] = src[e];
+  }
+  __syncthreads();
+  if (t == 0)
+    for (int c = 0; c < C3; ++c) s_cnt[s_map[c]] += 1.0f;
+  __syncthreads();
+  if (t < rows) {
+    const float* x = s_x + t * st3;
+    float* l2 = s_l2 + t * st2;
+    for (int g = 0; g < C2; ++g) l2[g] = reduce == 2 ? -INFINITY : 0.0f;
+    for (int c = 0; c < C3; ++c) {
+      const int g = s_map[c];
+      l2[g] = reduce == 2 ? logaddexp_ref(l2[g], x[c]) : l2[g] + x[c];
+    }
+    if (reduce == 1)
+      for (int g = 0; g < C2; ++g) l2[g] = l2[g] / fmaxf(s_cnt[g], 1.0f);
+    const long row = row0 + t;
+    if (k > 0) thread_topk(l2, C2, k, topk_idx + row * k, topk_val != nullptr ? topk_val + row * k : nullptr, nullptr, 0.f, 0.f);
+    if (top3_idx != nullptr || top3_prob != nullptr) {
+      float m = -INFINITY;
+      for (int c = 0; c < C3; ++c) m = fmaxf(m, x[c]);
+      float sum = 0.f;
+      for (int c = 0; c < C3; ++c) sum += expf(x[c] - m);
+      thread_topk(x, C3, C3 < 3 ? C3 : 3, top3_idx != nullptr ? top3_idx + row * 3 : nullptr, nullptr,
+                  top3_prob != nullptr ? top3_prob + row * 3 : nullptr, m, 1.0f / sum);
+    }
+  }
+  if (logits_l2_out != nullptr) {
+    __syncthreads();
+    float* dst = logits_l2_out + row0 * C2;
+    for (int e = t; e < rows * C2; e += 128) {
+      const int r = e / C2;
+      dst[e] = s_l2[r * st2 + (e - r * C2)];
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_transpose16(const void* src, void* dst, int R, int Cc, cudaStream_t stream) {
@@ -392,6 +572,25 @@ cudaError_t launch_topk(const float* logits, int rows, int cols, int k, int64_t*
   if (rows <= 0) return cudaSuccess;
   if (k <= 0 || k > cols) return cudaErrorInvalidValue;
   topk_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(logits, rows, cols, k, idx, val);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_l2_metrics(const float* logits_l3, int n, int C3, const int* l3_to_l2, int C2, int reduce, int k,
+                              float* logits_l2_out, int64_t* topk_idx, float* topk_val, int64_t* top3_idx,
+                              float* top3_prob, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (C3 <= 0 || C3 > L2M_MAX_C3 || C2 <= 0 || C2 > L2M_MAX_C2 || reduce < 0 || reduce > 2 || k < 0 || k > C2 ||
+      (k > 0 && topk_idx == nullptr))
+    return cudaErrorInvalidValue;
+  const size_t small = (static_cast<size_t>(128) * ((C3 | 1) + (C2 | 1)) + C3 + C2) * sizeof(float);
+  if (small <= 48 * 1024) {  // thread per row (the shipped 20 -> 11 map: 16 KB)
+    l2_metrics_small_kernel<<<(n + 127) / 128, 128, small, stream>>>(logits_l3, n, C3, l3_to_l2, C2, reduce, k,
+                                                                     logits_l2_out, topk_idx, topk_val, top3_idx, top3_prob);
+    return cudaGetLastError();
+  }
+  const size_t smem = (static_cast<size_t>(C3) + 4 * (C3 + C2)) * sizeof(float);
+  l2_metrics_kernel<<<(n + 3) / 4, 128, smem, stream>>>(logits_l3, n, C3, l3_to_l2, C2, reduce, k, logits_l2_out, topk_idx,
+                                                        topk_val, top3_idx, top3_prob);
   return cudaGetLastError();
 }
 

@@ -11,6 +11,13 @@ import torch
 import torch.nn.functional as F
 
 
+def _fused_ok(logits: torch.Tensor, num_l2: int) -> bool:
+    """fp32 CUDA logits within the limits of the fused metrics kernel (aihab_l2_metrics); other inputs take the
+    reference's torch formulation below, which also defines the semantics for fp16 / CPU tensors."""
+    return (logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2 and 1 <= logits.shape[1] <= 1024
+            and 1 <= num_l2 <= 256)
+
+
 def cls_acc(output: torch.Tensor, target: torch.Tensor, topk: int = 1) -> float:
     """ref methods/utils.py:16-21 — top-k accuracy in percent."""
     pred = output.topk(topk, 1, True, True)[1].t()
@@ -36,6 +43,9 @@ def aggregate_logits_to_l2(logits_l3: torch.Tensor, l3_to_l2: Union[Sequence[int
         raise ValueError(f"logits_l3 has {int(logits_l3.shape[1])} classes, but l3_to_l2 has {len(l3_list)} entries.")
     if reduce not in {"sum", "mean", "logsumexp"}:
         raise ValueError(f"Unsupported reduce='{reduce}'. Expected one of: sum, mean, logsumexp.")
+    if _fused_ok(logits_l3, num_l2) and all(0 <= int(v) < num_l2 for v in l3_list):
+        from . import ops  # one launch instead of a Python loop of C3 slice updates
+        return ops.l2_metrics(logits_l3, l3_list, num_l2, reduce, k=0, want_top3=False)[0]
     shape = (logits_l3.shape[0], num_l2)
     if reduce == "logsumexp":
         out = torch.full(shape, float("-inf"), device=logits_l3.device, dtype=logits_l3.dtype)
@@ -100,9 +110,15 @@ class L2MetricsAccumulator:
             preds = map_l3_targets_to_l2(logits_l3.argmax(dim=1), self.l3_to_l2)
             self.correct_at_k[1] += int((preds == targets_l2).sum().item())
         else:
-            logits_l2 = aggregate_logits_to_l2(logits_l3, self.l3_to_l2, self.num_l2, reduce=self.reduce)
             max_k = min(max(self.topk), self.num_l2)
-            correct = logits_l2.topk(max_k, dim=1).indices.eq(targets_l2.view(-1, 1))
+            if _fused_ok(logits_l3, self.num_l2) and self.reduce in {"sum", "mean", "logsumexp"}:
+                from . import ops  # aggregation + top-k in one launch
+                logits_l2, top_idx, _, _, _ = ops.l2_metrics(logits_l3, self.l3_to_l2, self.num_l2, self.reduce,
+                                                             k=max_k, want_top3=False)
+            else:
+                logits_l2 = aggregate_logits_to_l2(logits_l3, self.l3_to_l2, self.num_l2, reduce=self.reduce)
+                top_idx = logits_l2.topk(max_k, dim=1).indices
+            correct = top_idx.eq(targets_l2.view(-1, 1))
             for k in self.topk:
                 k_eff = min(k, max_k)
                 if k_eff >= 1:
@@ -139,7 +155,12 @@ class ClassificationTracker:
         self.accurate_classified = []
 
     def top3_metrics(self, outputs: torch.Tensor, labels: torch.Tensor):
-        top3_pred_indices = torch.topk(outputs, 3, dim=1).indices
-        top3_probs = torch.gather(F.softmax(outputs, dim=1), 1, top3_pred_indices)
+        if _fused_ok(outputs, min(int(outputs.shape[1]), 256)) and 3 <= outputs.shape[1] <= 256:
+            from . import ops  # top-3 + softmax probabilities in one launch (identity L3 -> L2 map)
+            _, _, _, top3_pred_indices, top3_probs = ops.l2_metrics(outputs, range(outputs.shape[1]), outputs.shape[1],
+                                                                    "sum", k=0, want_logits=False)
+        else:
+            top3_pred_indices = torch.topk(outputs, 3, dim=1).indices
+            top3_probs = torch.gather(F.softmax(outputs, dim=1), 1, top3_pred_indices)
         top3_correct = torch.sum(torch.any(top3_pred_indices == labels.unsqueeze(1), dim=1))
         return top3_correct, top3_pred_indices, top3_probs

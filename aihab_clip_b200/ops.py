@@ -125,3 +125,32 @@ def score16(feats16: torch.Tensor, proj16: torch.Tensor, text_w: torch.Tensor, s
                                    _ptr(emb), _ptr(logits), _ptr(idx), _ptr(val), _stream(dev))
     _lib.check(rc, "aihab_score16")
     return emb, logits, idx, val
+
+
+_REDUCE = {"sum": 0, "mean": 1, "logsumexp": 2}
+
+
+def l2_metrics(logits_l3: torch.Tensor, l3_to_l2, num_l2: int, reduce: str = "mean", k: int = 1,
+               want_logits: bool = True, want_top3: bool = True):
+    """Fused metrics epilogue (aihab_utils/evaluation.py:92-142, 186-221, 261-273) on a CUDA logits tensor [n, C3].
+    Returns (logits_l2 [n, num_l2] | None, topk_idx [n, k] int64, topk_val [n, k], top3_idx [n, 3] | None,
+    top3_prob [n, 3] | None)."""
+    _need_cuda(logits_l3)
+    if reduce not in _REDUCE:
+        raise ValueError(f"Unsupported reduce='{reduce}'. Expected one of: sum, mean, logsumexp.")
+    x = logits_l3.float().contiguous()
+    n, c3 = x.shape
+    dev = x.device
+    lut = (l3_to_l2.to(device=dev, dtype=torch.int32) if torch.is_tensor(l3_to_l2)
+           else torch.tensor(list(l3_to_l2), device=dev, dtype=torch.int32)).contiguous()
+    if lut.numel() != c3:
+        raise ValueError(f"logits_l3 has {c3} classes, but l3_to_l2 has {lut.numel()} entries.")
+    out = torch.empty(n, num_l2, dtype=torch.float32, device=dev) if want_logits else None
+    idx = torch.empty(n, k, dtype=torch.int64, device=dev) if k > 0 else None
+    val = torch.empty(n, k, dtype=torch.float32, device=dev) if k > 0 else None
+    t3i = torch.zeros(n, 3, dtype=torch.int64, device=dev) if want_top3 else None
+    t3p = torch.zeros(n, 3, dtype=torch.float32, device=dev) if want_top3 else None
+    rc = _lib.load().aihab_l2_metrics(_ptr(x), n, c3, _ptr(lut), int(num_l2), _REDUCE[reduce], k, _ptr(out), _ptr(idx),
+                                      _ptr(val), _ptr(t3i), _ptr(t3p), _stream(dev))
+    _lib.check(rc, "aihab_l2_metrics")
+    return out, idx, val, t3i, t3p

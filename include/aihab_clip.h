@@ -155,6 +155,16 @@ AIHAB_API int aihab_score16(const void* feats16, int n, int D, int dtype, const 
                             int C, float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx,
                             float* topk_val, void* stream);
 
+/* Metrics epilogue after the logits, one launch (aihab_utils/evaluation.py): aggregate_logits_to_l2 (:92-142,
+ * reduce 0 = sum, 1 = mean, 2 = logsumexp, accumulated in L3-id order like the reference loop), the top-k over the
+ * L2 logits that L2MetricsAccumulator.update takes (:186-221), and top3_metrics (:261-273): top-3 indices of the L3
+ * logits with their softmax probabilities.  l3_to_l2: device int32 [C3] (the L3 -> L2 label map, 20 -> 11 as shipped).
+ * Outputs (all nullable except topk_idx when k > 0): logits_l2_out [n,C2], topk_idx [n,k] int64 / topk_val [n,k],
+ * top3_idx [n,3] int64, top3_prob [n,3].  C3 <= 1024, C2 <= 256, k <= C2. */
+AIHAB_API int aihab_l2_metrics(const float* logits_l3, int n, int C3, const int32_t* l3_to_l2, int C2, int reduce, int k,
+                               float* logits_l2_out, int64_t* topk_idx, float* topk_val, int64_t* top3_idx,
+                               float* top3_prob, void* stream);
+
 /* Building blocks (exported for per-kernel parity tests; same kernels the tower uses) ---------------------- */
 /* D[M,N] = A[M,K] * W[N,K]^T with a fused epilogue; A, W 16-bit (ab_dtype), K % 8 == 0. */
 AIHAB_API int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype, int epilogue, const float* bias,

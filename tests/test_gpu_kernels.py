@@ -228,3 +228,62 @@ def test_score16_tensor_core_path(cuda_device, dtype, n, D, E, Cn, k):
     _, l32, i32, _ = ops.score(feats.to(cuda_device).float(), proj.to(cuda_device).float(),
                                torch.from_numpy(tw).to(cuda_device), 100.0, k)
     np.testing.assert_allclose(logits.cpu().numpy(), l32.cpu().numpy(), atol=5e-4, rtol=0)
+
+
+@pytest.mark.parametrize("n,C3,C2,k", [(257, 20, 11, 3), (5, 20, 11, 1), (4097, 37, 5, 5), (64, 1000, 100, 5)])
+@pytest.mark.parametrize("reduce", ["sum", "mean", "logsumexp"])
+def test_l2_metrics_match_oracle(cuda_device, n, C3, C2, k, reduce):
+    """Fused L3 -> L2 aggregation + top-k + top-3 / softmax probabilities (aihab_utils/evaluation.py:92-142, 186-221,
+    261-273) against the numpy restatement: sum / mean bit-exact (same accumulation order), logsumexp and the
+    probabilities to 2e-6 relative, indices exact wherever the oracle's scores are untied."""
+    _lib, ops = _ops()
+    rng = np.random.default_rng(n * 31 + C3)
+    logits = (100.0 * rng.uniform(-0.3, 0.3, (n, C3))).astype(np.float32)
+    logits[0, :] = logits[0, 0]  # a fully tied row: lowest index first
+    lut = rng.integers(0, C2, C3)
+    lut[:min(C2, C3)] = np.arange(min(C2, C3))  # every group that can be populated is
+    out, idx, val, t3i, t3p = ops.l2_metrics(torch.from_numpy(logits).to(cuda_device), lut.tolist(), C2, reduce, k=k)
+    ref = O.aggregate_logits_to_l2(logits, lut, C2, reduce)
+    got = out.cpu().numpy()
+    if reduce == "logsumexp":
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), fin)
+        np.testing.assert_allclose(got[fin], ref[fin], rtol=2e-6, atol=2e-6)
+    else:
+        np.testing.assert_array_equal(got, ref)
+    ref_idx = O.topk_indices(got, k)  # ordering rule checked on the kernel's own L2 logits
+    np.testing.assert_array_equal(idx.cpu().numpy(), ref_idx)
+    np.testing.assert_array_equal(val.cpu().numpy(), np.take_along_axis(got, ref_idx, axis=1))
+    _, r3i, r3p = O.top3_metrics(logits, np.zeros(n, dtype=np.int64))
+    np.testing.assert_array_equal(t3i.cpu().numpy(), r3i)
+    np.testing.assert_allclose(t3p.cpu().numpy(), r3p, rtol=3e-6, atol=1e-9)
+
+
+def test_evaluation_mirrors_use_the_fused_kernel_on_cuda(cuda_device):
+    """L2MetricsAccumulator / ClassificationTracker / aggregate_logits_to_l2 give the same numbers on CUDA (fused
+    kernel) as on CPU (the reference's torch formulation)."""
+    from aihab_clip_b200 import evaluation as E
+    _lib, _ = _ops()
+    rng = np.random.default_rng(5)
+    logits = torch.from_numpy((100.0 * rng.uniform(-0.3, 0.3, (300, 20))).astype(np.float32))
+    targets = torch.from_numpy(rng.integers(0, 20, 300))
+    lut = [0, 0, 1, 2, 2, 3, 4, 5, 5, 5, 6, 7, 8, 8, 9, 10, 10, 3, 1, 0]
+    n0 = _lib.kernel_launches()
+    for reduce in ("sum", "mean", "logsumexp"):
+        a = E.aggregate_logits_to_l2(logits, lut, 11, reduce)
+        b = E.aggregate_logits_to_l2(logits.to(cuda_device), lut, 11, reduce).cpu()
+        if reduce == "logsumexp":
+            torch.testing.assert_close(b, a, rtol=2e-6, atol=2e-6)
+        else:
+            assert torch.equal(a, b)
+        acc_c = E.L2MetricsAccumulator(lut, 11, reduce=reduce, topk=(1, 3), mode="logits")
+        acc_g = E.L2MetricsAccumulator(lut, 11, reduce=reduce, topk=(1, 3), mode="logits")
+        acc_c.update(logits, targets)
+        acc_g.update(logits.to(cuda_device), targets.to(cuda_device))
+        mc, mg = acc_c.compute(), acc_g.compute()
+        assert mc["top1"] == mg["top1"] and mc["top3"] == mg["top3"] and mc["f1"] == mg["f1"]
+    c_cpu, i_cpu, p_cpu = E.ClassificationTracker().top3_metrics(logits, targets)
+    c_gpu, i_gpu, p_gpu = E.ClassificationTracker().top3_metrics(logits.to(cuda_device), targets.to(cuda_device))
+    assert int(c_cpu) == int(c_gpu) and torch.equal(i_cpu, i_gpu.cpu())
+    torch.testing.assert_close(p_gpu.cpu(), p_cpu, rtol=3e-6, atol=1e-9)
+    assert _lib.kernel_launches() > n0  # the CUDA calls went through libaihab_clip.so

@@ -78,6 +78,27 @@ def main():
     ms = time_steps(lambda: ops.score16(f16, p16, tw, 100.0, 5), 3, warm=1)
     rows.append({"config": f"scoring {n} x 768 fp16 cache -> proj 512 -> 1000 classes -> top-5 (tcgen05, exact products + hi/lo split)",
                  "ms_per_step": round(ms, 2), "rows_per_s": round(n / ms * 1e3), "tflops_algorithmic": round(2.0 * n * (768 * 512 + 512 * 1000) / ms / 1e9, 1)})
+    # L3 -> L2 aggregation + top-k + top-3 / softmax probabilities after the logits
+    del feats, f16
+    from aihab_clip_b200 import evaluation as E
+    lut = torch.tensor([0, 0, 1, 2, 2, 3, 4, 5, 5, 5, 6, 7, 8, 8, 9, 10, 10, 3, 1, 0], device=dev, dtype=torch.int32)
+    lg = 30.0 * torch.randn(n, 20, device=dev)
+    ms = time_steps(lambda: ops.l2_metrics(lg, lut, 11, "mean", k=3), 10, warm=2)
+    algo = n * (20 * 4 + 11 * 4 + 3 * 12 + 3 * 12)
+    E_fused = E._fused_ok
+    E._fused_ok = lambda *a: False  # the reference's torch formulation (Python loop over the 20 classes)
+
+    def torch_path():
+        l2 = E.aggregate_logits_to_l2(lg, lut, 11, "mean")
+        l2.topk(3, dim=1)
+        E.ClassificationTracker().top3_metrics(lg, torch.zeros(n, dtype=torch.long, device=dev))
+
+    ms_t = time_steps(torch_path, 3, warm=1)
+    E._fused_ok = E_fused
+    rows.append({"config": f"L3->L2 metrics epilogue {n} x 20 -> 11 (mean) + top-3 + top-3 softmax probs (one launch)",
+                 "ms_per_step": round(ms, 3), "rows_per_s": round(n / ms * 1e3), "gbs_algorithmic": round(algo / ms / 1e6, 1),
+                 "frac_of_hbm_peak": round(algo / ms / 1e6 / peaks["hbm"], 3),
+                 "torch_formulation_ms": round(ms_t, 3)})
     for r in rows:
         print(json.dumps(r))
 
