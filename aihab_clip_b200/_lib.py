@@ -28,6 +28,15 @@ class BlockWeights(C.Structure):
         "ln_2_weight", "ln_2_bias", "c_fc_weight", "c_fc_bias", "c_proj_weight", "c_proj_bias")]
 
 
+class TextConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("context_length", "vocab_size", "width", "layers", "heads", "dtype", "max_batch")]
+
+
+class TextWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("token_embedding", "positional_embedding", "ln_final_weight",
+                                          "ln_final_bias")] + [("blocks", C.POINTER(BlockWeights))]
+
+
 class VitWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "conv1_weight", "class_embedding", "positional_embedding", "ln_pre_weight", "ln_pre_bias",
@@ -52,6 +61,10 @@ SIGNATURES = {
                               C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "aihab_score16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float,
                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "aihab_text_create": (C.c_int, [C.POINTER(TextConfig), C.POINTER(TextWeights), C.c_int, C.POINTER(C.c_void_p)]),
+    "aihab_text_destroy": (None, [C.c_void_p]),
+    "aihab_text_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "aihab_attention_causal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aihab_l2_metrics": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "aihab_gemm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -125,6 +125,56 @@ class _Engine:
             pass
 
 
+class _TextEngine:
+    """Owns one aihab_text handle: the text transformer of a CLIP model on the tensor-core kernels (causal mask)."""
+
+    def __init__(self, clip: "CLIP", device: torch.device, dtype_code: int, max_batch: int):
+        lib = _lib.load()
+        keep = []
+
+        def f32(t):
+            t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return C.c_void_p(t.data_ptr())
+
+        tr = clip.transformer
+        blocks = (_lib.BlockWeights * tr.layers)()
+        for i, b in enumerate(tr.resblocks):
+            blocks[i] = _lib.BlockWeights(
+                f32(b.ln_1.weight), f32(b.ln_1.bias), f32(b.attn.in_proj_weight), f32(b.attn.in_proj_bias),
+                f32(b.attn.out_proj.weight), f32(b.attn.out_proj.bias), f32(b.ln_2.weight), f32(b.ln_2.bias),
+                f32(b.mlp.c_fc.weight), f32(b.mlp.c_fc.bias), f32(b.mlp.c_proj.weight), f32(b.mlp.c_proj.bias))
+        w = _lib.TextWeights(f32(clip.token_embedding.weight), f32(clip.positional_embedding),
+                             f32(clip.ln_final.weight), f32(clip.ln_final.bias), blocks)
+        cfg = _lib.TextConfig(clip.context_length, clip.vocab_size, tr.width, tr.layers, tr.width // 64, dtype_code,
+                              max_batch)
+        handle = C.c_void_p()
+        torch.cuda.synchronize(device)
+        _lib.check(lib.aihab_text_create(C.byref(cfg), C.byref(w), device.index, C.byref(handle)), "aihab_text_create")
+        self._lib, self.handle, self.device, self.width = lib, handle, device, tr.width
+        del keep  # the handle owns packed copies
+
+    def encode(self, tokens: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+        tokens = tokens.to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty(tokens.shape[0], self.width, dtype=out_dtype, device=self.device)
+        rc = self._lib.aihab_text_encode(self.handle, C.c_void_p(tokens.data_ptr()), tokens.shape[0],
+                                         C.c_void_p(out.data_ptr()), ops.dtype_code(out_dtype),
+                                         C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        _lib.check(rc, "aihab_text_encode")
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.aihab_text_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover - interpreter teardown order
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class VisionTransformer(nn.Module):
     """ref clip/model.py:199-235.  Same constructor, same parameter names; forward runs in libaihab_clip.so."""
 
@@ -232,6 +282,13 @@ class CLIP(nn.Module):
         self.ln_final = LayerNorm(transformer_width)
         self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim))
         self.logit_scale = nn.Parameter(torch.ones([]) * 2.659260036932778)  # log(1 / 0.07)
+        # engine knob (not part of the reference protocol): "torch" keeps the text tower in PyTorch at the model dtype
+        # (the default: it runs once per class set), "b200" runs it on the tensor-core kernels (16-bit operands) for
+        # large prompt ensembles
+        self.text_engine = os.environ.get("AIHAB_CLIP_TEXT_ENGINE", "torch")
+        self.text_max_batch = int(os.environ.get("AIHAB_CLIP_TEXT_MAX_BATCH", "512"))
+        self._tengine = None
+        self._tengine_key = None
         self._init_text()
 
     def _init_text(self):  # ref :294-321
@@ -256,7 +313,25 @@ class CLIP(nn.Module):
         """Extension: raw uint8 HWC batch -> features (GPU preprocessing fused in front of the tower)."""
         return self.visual.forward_u8(images_u8, self.dtype)
 
+    def _text_engine(self, device: torch.device) -> _TextEngine:
+        params = [self.token_embedding.weight, self.positional_embedding, self.ln_final.weight, self.ln_final.bias]
+        params += list(self.transformer.parameters())
+        key = (device, self.visual.compute_dtype, self.text_max_batch, tuple((p.data_ptr(), p._version) for p in params))
+        if self._tengine is None or self._tengine_key != key:
+            if self._tengine is not None:
+                self._tengine.close()
+            self._tengine = _TextEngine(self, device, _COMPUTE_DTYPES[self.visual.compute_dtype], self.text_max_batch)
+            self._tengine_key = key
+        return self._tengine
+
     def encode_text(self, text: torch.Tensor):
+        if self.text_engine == "b200":  # ref :338-353 on libaihab_clip.so; same return contract
+            if not text.is_cuda:
+                raise RuntimeError("text_engine='b200' runs on a CUDA device only (no CPU fallback); move the tokens "
+                                   "to 'cuda' or use text_engine='torch'")
+            with torch.no_grad():
+                x_before_proj = self._text_engine(text.device).encode(text, self.dtype)
+            return x_before_proj, x_before_proj @ self.text_projection
         x = self.token_embedding(text).type(self.dtype)
         x = x + self.positional_embedding.type(self.dtype)
         x = self.transformer(x)

@@ -311,6 +311,10 @@ struct aihab_vit {
   CUtensorMap m_patches, m_y, m_h, m_x;  // m_x: fp32 residual stream, {32,32} boxes (EPI_BIAS_RES_32)
   CUtensorMap m_attn_q, m_attn_kv;       // qkv view [cap_rows, 3D] of `big` for the tcgen05 attention
   int attn_kind = 0;
+  int causal = 0;  // text tower: key j visible to query i only for j <= i (clip/model.py:323-329)
+  // text tower ends (aihab_text_*): embedding table, ln_final, EOT rows
+  float *tok_emb = nullptr, *lnf_g = nullptr, *lnf_b = nullptr, *xe = nullptr;
+  int vocab = 0;
   // side stream for the few query rows the flash attention leaves to the SIMT row kernel (L = 257): it runs
   // concurrently with the tensor-core kernel, fork / join through the two events
   cudaStream_t side = nullptr;
@@ -428,17 +432,9 @@ int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], in
   return 0;
 }
 
-// transformer stack + ln_post on a chunk of n images whose patch rows are already in h->patches
-int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t s) {
+// the residual attention blocks (clip/model.py:165-197) on the M = n * L rows of the fp32 residual stream h->x
+int run_blocks(aihab_vit* h, int n, cudaStream_t s) {
   const int D = h->D, L = h->L, M = n * L;
-  // conv1 as GEMM + positional embedding (clip/model.py:217-221)
-  if (run_gemm(h, h->m_patches, h->m_conv, n * h->g2, D, h->Kpad, aihab::EPI_PATCH_32, nullptr, nullptr, h->x, D, s))
-    return 1;
-  // class token row + ln_pre, in place on the fp32 residual stream (clip/model.py:220-222)
-  {
-    ProfScope ps(PC_LN, 8.0 * M * D, s);
-    CKL(aihab::launch_layernorm(h->x, D, h->cls0, L, h->lnpre_g, h->lnpre_b, h->x, nullptr, 0, M, D, s));
-  }
   const int layers = static_cast<int>(h->blocks.size());
   int nsb = 0;  // stat blocks per row written by the last residual GEMM
   // Zig-zag traversal: each kernel walks the token rows in the direction opposite to its producer, so the ~100 MB the
@@ -486,7 +482,7 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
       }
       else if (h->attn_kind == 2)
         CKL(aihab::launch_attention_tcp(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, h->num_sms, s,
-                                        next_dir()));
+                                        next_dir(), h->causal));
       else if (h->attn_kind == 1)
         CKL(aihab::launch_attention_tc(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, s));
       else
@@ -522,11 +518,100 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
         return 1;
     }
   }
+  return 0;
+}
+
+// transformer stack + ln_post on a chunk of n images whose patch rows are already in h->patches
+int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t s) {
+  const int D = h->D, L = h->L, M = n * L;
+  // conv1 as GEMM + positional embedding (clip/model.py:217-221)
+  if (run_gemm(h, h->m_patches, h->m_conv, n * h->g2, D, h->Kpad, aihab::EPI_PATCH_32, nullptr, nullptr, h->x, D, s))
+    return 1;
+  // class token row + ln_pre, in place on the fp32 residual stream (clip/model.py:220-222)
+  {
+    ProfScope ps(PC_LN, 8.0 * M * D, s);
+    CKL(aihab::launch_layernorm(h->x, D, h->cls0, L, h->lnpre_g, h->lnpre_b, h->x, nullptr, 0, M, D, s));
+  }
+  if (run_blocks(h, n, s)) return 1;
   // ln_post on token 0 of every image (clip/model.py:228); rows are L*D apart
   float* o32 = out_dtype == AIHAB_F32 ? static_cast<float*>(feats_out) : nullptr;
   void* o16 = out_dtype == AIHAB_F32 ? nullptr : feats_out;
   CKL(aihab::launch_layernorm(h->x, static_cast<size_t>(L) * D, nullptr, 0, h->lnpost_g, h->lnpost_b, o32, o16,
                               out_dtype == AIHAB_BF16, n, D, s));
+  return 0;
+}
+
+// Common part of the two towers: packs the residual attention blocks, allocates the activation workspace for
+// h->cap_rows token rows (+ patch_rows im2col rows for the image tower) and builds the TMA descriptors.
+// Returns non-zero after fail(); the caller destroys the handle.
+int build_stack(aihab_vit* h, int layers, const aihab_vit_block_weights* blocks, size_t patch_rows) {
+  const int D = h->D, L = h->L;
+  {
+    const char* e = getenv("AIHAB_LNFOLD");
+    h->ln_fold = !(e && e[0] == '0') && D / 128 <= kMaxStatBlocks;
+    const char* z = getenv("AIHAB_ZIGZAG");
+    h->zigzag = !(z && z[0] == '0');
+  }
+  h->blocks.resize(layers);
+  for (int i = 0; i < layers; ++i) {
+    const aihab_vit_block_weights& s = blocks[i];
+    aihab_vit::Block& b = h->blocks[i];
+    if (upload_16(h, s.in_proj_weight, 3 * D, D, D, &b.w_in) || upload_16(h, s.out_proj_weight, D, D, D, &b.w_out) ||
+        upload_16(h, s.c_fc_weight, 4 * D, D, D, &b.w_fc) || upload_16(h, s.c_proj_weight, D, 4 * D, 4 * D, &b.w_proj))
+      return 1;
+    if (upload_f32(h, s.in_proj_bias, 3 * D, &b.b_in) || upload_f32(h, s.out_proj_bias, D, &b.b_out) ||
+        upload_f32(h, s.c_fc_bias, 4 * D, &b.b_fc) || upload_f32(h, s.c_proj_bias, D, &b.b_proj) ||
+        upload_f32(h, s.ln_1_weight, D, &b.ln1_g) || upload_f32(h, s.ln_1_bias, D, &b.ln1_b) ||
+        upload_f32(h, s.ln_2_weight, D, &b.ln2_g) || upload_f32(h, s.ln_2_bias, D, &b.ln2_b))
+      return 1;
+    if (weight_maps(h, b.w_in, 3 * D, D, b.m_in) || weight_maps(h, b.w_out, D, D, b.m_out) ||
+        weight_maps(h, b.w_fc, 4 * D, D, b.m_fc) || weight_maps(h, b.w_proj, D, 4 * D, b.m_proj))
+      return 1;
+    if (h->ln_fold &&
+        (fold_ln(h, s.in_proj_weight, s.in_proj_bias, s.ln_1_weight, s.ln_1_bias, 3 * D, D, &b.s_in, &b.bp_in) ||
+         fold_ln(h, s.c_fc_weight, s.c_fc_bias, s.ln_2_weight, s.ln_2_bias, 4 * D, D, &b.s_fc, &b.bp_fc)))
+      return 1;
+  }
+  // workspace
+  const size_t prow = patch_rows;
+  if ((prow > 0 && dev_alloc(h, &h->patches, prow * h->Kpad * 2)) ||
+      dev_alloc(h, reinterpret_cast<void**>(&h->x), h->cap_rows * D * 4) || dev_alloc(h, &h->y, h->cap_rows * D * 2) ||
+      dev_alloc(h, &h->big, h->cap_rows * 4 * D * 2) || dev_alloc(h, &h->y2, h->cap_rows * D * 2) ||
+      dev_alloc(h, reinterpret_cast<void**>(&h->ln_stats), h->cap_rows * kMaxStatBlocks * 2 * sizeof(float)))
+    return 1;
+  if ((prow > 0 && cudaMemset(h->patches, 0, prow * h->Kpad * 2) != cudaSuccess) || cudaMemset(h->y, 0, h->cap_rows * D * 2) != cudaSuccess ||
+      cudaMemset(h->big, 0, h->cap_rows * 4 * D * 2) != cudaSuccess ||
+      cudaMemset(h->y2, 0, h->cap_rows * D * 2) != cudaSuccess) {
+    fail("aihab_vit_create: cudaMemset failed");
+    return 1;
+  }
+  if ((prow > 0 && aihab::make_tmap_2d_16bit(&h->m_patches, h->patches, prow, h->Kpad, static_cast<uint64_t>(h->Kpad) * 2, 128,
+                                             h->bf16) != cudaSuccess) ||
+      aihab::make_tmap_2d_16bit(&h->m_y, h->y, h->cap_rows, D, static_cast<uint64_t>(D) * 2, 128, h->bf16) != cudaSuccess ||
+      aihab::make_tmap_2d_16bit(&h->m_h, h->big, h->cap_rows, 4 * D, static_cast<uint64_t>(4 * D) * 2, 128, h->bf16) != cudaSuccess ||
+      aihab::make_tmap_2d_16bit(&h->m_y2, h->y2, h->cap_rows, D, static_cast<uint64_t>(D) * 2, 128, h->bf16) != cudaSuccess ||
+      aihab::make_tmap_2d_f32_box32(&h->m_x, h->x, h->cap_rows, D, static_cast<uint64_t>(D) * 4) != cudaSuccess) {
+    fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the workspace");
+    return 1;
+  }
+  h->attn_kind = attention_kind(L);
+  if (h->attn_kind == 3 && aihab::attention_tcf_tail_rows(L) > 0 && getenv("AIHAB_ATTN_SERIAL_TAIL") == nullptr) {
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      fail("aihab_vit_create: could not create the attention side stream");
+      return 1;
+    }
+  }
+  if (h->attn_kind > 0) {
+    const uint64_t pitch = static_cast<uint64_t>(3 * D) * 2;
+    if (aihab::make_tmap_2d_16bit(&h->m_attn_q, h->big, h->cap_rows, 3 * D, pitch, 128, h->bf16) != cudaSuccess ||
+        aihab::make_tmap_2d_16bit(&h->m_attn_kv, h->big, h->cap_rows, 3 * D, pitch,
+                                  attention_key_box(h->attn_kind, L), h->bf16) != cudaSuccess) {
+      fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the attention views");
+      return 1;
+    }
+  }
   return 0;
 }
 
@@ -637,71 +722,7 @@ int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, in
     for (int i = 0; i < D; ++i) cls[i] += p0[i];
     if (upload_f32(h, cls.data(), D, &h->cls0)) return bail(1);
   }
-  {
-    const char* e = getenv("AIHAB_LNFOLD");
-    h->ln_fold = !(e && e[0] == '0') && D / 128 <= kMaxStatBlocks;
-    const char* z = getenv("AIHAB_ZIGZAG");
-    h->zigzag = !(z && z[0] == '0');
-  }
-  h->blocks.resize(cfg->layers);
-  for (int i = 0; i < cfg->layers; ++i) {
-    const aihab_vit_block_weights& s = w->blocks[i];
-    aihab_vit::Block& b = h->blocks[i];
-    if (upload_16(h, s.in_proj_weight, 3 * D, D, D, &b.w_in) || upload_16(h, s.out_proj_weight, D, D, D, &b.w_out) ||
-        upload_16(h, s.c_fc_weight, 4 * D, D, D, &b.w_fc) || upload_16(h, s.c_proj_weight, D, 4 * D, 4 * D, &b.w_proj))
-      return bail(1);
-    if (upload_f32(h, s.in_proj_bias, 3 * D, &b.b_in) || upload_f32(h, s.out_proj_bias, D, &b.b_out) ||
-        upload_f32(h, s.c_fc_bias, 4 * D, &b.b_fc) || upload_f32(h, s.c_proj_bias, D, &b.b_proj) ||
-        upload_f32(h, s.ln_1_weight, D, &b.ln1_g) || upload_f32(h, s.ln_1_bias, D, &b.ln1_b) ||
-        upload_f32(h, s.ln_2_weight, D, &b.ln2_g) || upload_f32(h, s.ln_2_bias, D, &b.ln2_b))
-      return bail(1);
-    if (weight_maps(h, b.w_in, 3 * D, D, b.m_in) || weight_maps(h, b.w_out, D, D, b.m_out) ||
-        weight_maps(h, b.w_fc, 4 * D, D, b.m_fc) || weight_maps(h, b.w_proj, D, 4 * D, b.m_proj))
-      return bail(1);
-    if (h->ln_fold &&
-        (fold_ln(h, s.in_proj_weight, s.in_proj_bias, s.ln_1_weight, s.ln_1_bias, 3 * D, D, &b.s_in, &b.bp_in) ||
-         fold_ln(h, s.c_fc_weight, s.c_fc_bias, s.ln_2_weight, s.ln_2_bias, 4 * D, D, &b.s_fc, &b.bp_fc)))
-      return bail(1);
-  }
-  // workspace
-  const size_t prow = static_cast<size_t>(cfg->max_batch) * h->g2;
-  if (dev_alloc(h, &h->patches, prow * h->Kpad * 2) ||
-      dev_alloc(h, reinterpret_cast<void**>(&h->x), h->cap_rows * D * 4) || dev_alloc(h, &h->y, h->cap_rows * D * 2) ||
-      dev_alloc(h, &h->big, h->cap_rows * 4 * D * 2) || dev_alloc(h, &h->y2, h->cap_rows * D * 2) ||
-      dev_alloc(h, reinterpret_cast<void**>(&h->ln_stats), h->cap_rows * kMaxStatBlocks * 2 * sizeof(float)))
-    return bail(1);
-  if (cudaMemset(h->patches, 0, prow * h->Kpad * 2) != cudaSuccess || cudaMemset(h->y, 0, h->cap_rows * D * 2) != cudaSuccess ||
-      cudaMemset(h->big, 0, h->cap_rows * 4 * D * 2) != cudaSuccess ||
-      cudaMemset(h->y2, 0, h->cap_rows * D * 2) != cudaSuccess) {
-    fail("aihab_vit_create: cudaMemset failed");
-    return bail(1);
-  }
-  if (aihab::make_tmap_2d_16bit(&h->m_patches, h->patches, prow, h->Kpad, static_cast<uint64_t>(h->Kpad) * 2, 128, h->bf16) != cudaSuccess ||
-      aihab::make_tmap_2d_16bit(&h->m_y, h->y, h->cap_rows, D, static_cast<uint64_t>(D) * 2, 128, h->bf16) != cudaSuccess ||
-      aihab::make_tmap_2d_16bit(&h->m_h, h->big, h->cap_rows, 4 * D, static_cast<uint64_t>(4 * D) * 2, 128, h->bf16) != cudaSuccess ||
-      aihab::make_tmap_2d_16bit(&h->m_y2, h->y2, h->cap_rows, D, static_cast<uint64_t>(D) * 2, 128, h->bf16) != cudaSuccess ||
-      aihab::make_tmap_2d_f32_box32(&h->m_x, h->x, h->cap_rows, D, static_cast<uint64_t>(D) * 4) != cudaSuccess) {
-    fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the workspace");
-    return bail(1);
-  }
-  h->attn_kind = attention_kind(L);
-  if (h->attn_kind == 3 && aihab::attention_tcf_tail_rows(L) > 0 && getenv("AIHAB_ATTN_SERIAL_TAIL") == nullptr) {
-    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-      fail("aihab_vit_create: could not create the attention side stream");
-      return bail(1);
-    }
-  }
-  if (h->attn_kind > 0) {
-    const uint64_t pitch = static_cast<uint64_t>(3 * D) * 2;
-    if (aihab::make_tmap_2d_16bit(&h->m_attn_q, h->big, h->cap_rows, 3 * D, pitch, 128, h->bf16) != cudaSuccess ||
-        aihab::make_tmap_2d_16bit(&h->m_attn_kv, h->big, h->cap_rows, 3 * D, pitch,
-                                  attention_key_box(h->attn_kind, L), h->bf16) != cudaSuccess) {
-      fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the attention views");
-      return bail(1);
-    }
-  }
+  if (build_stack(h, cfg->layers, w->blocks, static_cast<size_t>(cfg->max_batch) * h->g2)) return bail(1);
   CK(cudaDeviceSynchronize());
   *out = h;
   return 0;
@@ -718,6 +739,93 @@ void aihab_vit_destroy(aihab_vit* h) {
 }
 
 size_t aihab_vit_workspace_bytes(const aihab_vit* h) { return h ? h->ws_bytes : 0; }
+
+// ---- text tower: the same handle type with token-embedding ends instead of the patch-embedding ends
+int aihab_text_create(const aihab_text_config* cfg, const aihab_text_weights* w, int device, aihab_text** out) {
+  if (cfg == nullptr || w == nullptr || out == nullptr) return fail("aihab_text_create: null argument");
+  *out = nullptr;
+  if (cfg->context_length <= 64 || cfg->context_length > 224)
+    return fail("aihab_text_create: context_length must be in 65..224 (causal tcgen05 attention)");
+  if (cfg->width % 128 != 0 || cfg->width > 2048) return fail("aihab_text_create: width must be a multiple of 128, <= 2048");
+  if (cfg->heads * 64 != cfg->width) return fail("aihab_text_create: heads must equal width / 64");
+  if (cfg->dtype != AIHAB_F16 && cfg->dtype != AIHAB_BF16) return fail("aihab_text_create: dtype must be AIHAB_F16 or AIHAB_BF16");
+  if (cfg->layers <= 0 || cfg->max_batch <= 0 || cfg->vocab_size <= 0 || w->blocks == nullptr)
+    return fail("aihab_text_create: bad layers/max_batch/vocab_size/blocks");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail("aihab_text_create: no CUDA device (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return fail("aihab_text_create: bad device index");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("aihab_text_create: device is not sm_100 (Blackwell B200) — kernels are sm_100a only");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("aihab_text_create: cudaSetDevice failed");
+  CK(aihab::gemm_init());
+
+  aihab_vit* h = new aihab_vit();
+  h->cfg.width = cfg->width;
+  h->cfg.layers = cfg->layers;
+  h->cfg.heads = cfg->heads;
+  h->cfg.dtype = cfg->dtype;
+  h->cfg.max_batch = cfg->max_batch;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->L = cfg->context_length;
+  h->D = cfg->width;
+  h->bf16 = cfg->dtype == AIHAB_BF16;
+  h->cap_rows = static_cast<size_t>(cfg->max_batch) * h->L;
+  h->causal = 1;
+  h->vocab = cfg->vocab_size;
+  const int D = h->D, L = h->L;
+  auto bail = [&](int) {
+    aihab_vit_destroy(h);
+    return 1;
+  };
+  if (upload_f32(h, w->token_embedding, static_cast<size_t>(cfg->vocab_size) * D, &h->tok_emb) ||
+      upload_f32(h, w->positional_embedding, static_cast<size_t>(L) * D, &h->pos) ||
+      upload_f32(h, w->ln_final_weight, D, &h->lnf_g) || upload_f32(h, w->ln_final_bias, D, &h->lnf_b) ||
+      dev_alloc(h, reinterpret_cast<void**>(&h->xe), static_cast<size_t>(cfg->max_batch) * D * sizeof(float)))
+    return bail(1);
+  if (build_stack(h, cfg->layers, w->blocks, 0)) return bail(1);
+  if (h->attn_kind != 2) {
+    fail("aihab_text_create: the causal mask needs the persistent tcgen05 attention (AIHAB_ATTN must not cap it)");
+    return bail(1);
+  }
+  CK(cudaDeviceSynchronize());
+  *out = reinterpret_cast<aihab_text*>(h);
+  return 0;
+}
+
+void aihab_text_destroy(aihab_text* h) { aihab_vit_destroy(reinterpret_cast<aihab_vit*>(h)); }
+
+int aihab_text_encode(aihab_text* ht, const int64_t* tokens, int n, void* feats_out, int out_dtype, void* stream) {
+  aihab_vit* h = reinterpret_cast<aihab_vit*>(ht);
+  if (h == nullptr || !h->causal) return fail("aihab_text_encode: not a text handle");
+  if (n < 0 || out_dtype < 0 || out_dtype > 2) return fail("aihab_text_encode: bad argument");
+  if (n == 0) return 0;
+  if (tokens == nullptr || feats_out == nullptr) return fail("aihab_text_encode: null buffer");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int L = h->L, D = h->D;
+  for (int i0 = 0; i0 < n; i0 += h->cfg.max_batch) {
+    const int nb = std::min(h->cfg.max_batch, n - i0);
+    const int64_t* tk = tokens + static_cast<size_t>(i0) * L;
+    {  // x = token_embedding(text) + positional_embedding   (clip/model.py:341-342)
+      ProfScope ps(PC_PRE, static_cast<double>(nb) * L * D * 8.0, s);
+      CKL(aihab::launch_embed_tokens(tk, h->tok_emb, h->pos, h->x, static_cast<long>(nb) * L, L, D, h->vocab, s));
+    }
+    if (run_blocks(h, nb, s)) return 1;
+    // ln_final(x)[arange, text.argmax(-1)]   (clip/model.py:345, 350): gather the EOT rows, then LayerNorm on those
+    CKL(aihab::launch_eot_gather(tk, h->x, h->xe, nb, L, D, s));
+    void* dst = static_cast<uint8_t*>(feats_out) + static_cast<size_t>(i0) * D * dtype_size(out_dtype);
+    float* o32 = out_dtype == AIHAB_F32 ? static_cast<float*>(dst) : nullptr;
+    void* o16 = out_dtype == AIHAB_F32 ? nullptr : dst;
+    CKL(aihab::launch_layernorm(h->xe, D, nullptr, 0, h->lnf_g, h->lnf_b, o32, o16, out_dtype == AIHAB_BF16, nb, D, s));
+  }
+  return 0;
+}
 
 int aihab_preferred_batch(int tokens, int width, int max_batch, int device) {
   if (tokens <= 0 || width <= 0 || max_batch <= 0) return max_batch > 0 ? max_batch : 1;
@@ -992,6 +1100,23 @@ int aihab_layernorm(const float* x, int rows, int D, const float* gamma, const f
   DeviceGuard guard(device_of(x));
   CKL(aihab::launch_layernorm(x, D, nullptr, 0, gamma, beta, out32, out16, out16_dtype == AIHAB_BF16, rows, D,
                               static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int aihab_attention_causal(const void* qkv, void* out, int n, int L, int H, int dtype, void* stream) {
+  if (qkv == nullptr || out == nullptr || n < 0) return fail("aihab_attention_causal: bad argument");
+  if (dtype != AIHAB_F16 && dtype != AIHAB_BF16) return fail("aihab_attention_causal: dtype must be AIHAB_F16 or AIHAB_BF16");
+  if (!aihab::attention_tcp_supported(L)) return fail("aihab_attention_causal: needs 64 < L <= 224");
+  DeviceGuard guard(device_of(qkv));
+  if (n == 0) return 0;
+  CUtensorMap mq, mkv;
+  const int bf16 = dtype == AIHAB_BF16;
+  const uint64_t rows = static_cast<uint64_t>(n) * L, pitch = static_cast<uint64_t>(3 * H * 64) * 2;
+  CK(aihab::gemm_init());
+  CK(aihab::make_tmap_2d_16bit(&mq, qkv, rows, 3 * H * 64, pitch, 128, bf16));
+  CK(aihab::make_tmap_2d_16bit(&mkv, qkv, rows, 3 * H * 64, pitch, aihab::attention_tc_key_rows(L), bf16));
+  CKL(aihab::launch_attention_tcp(mq, mkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream),
+                                  0, 1));
   return 0;
 }
 

@@ -37,7 +37,9 @@ static_assert(P_SMEM <= 227 * 1024, "smem budget");
 // Softmax of one query row half for one item, fully unrolled over NC 16-column chunks: the S values are read from
 // TMEM ONCE (NC x tcgen05.ld.x16 in flight together) and stay in registers across the row-max exchange.
 // Columns >= L are masked; only the last two chunks of a thread's range can contain such columns.
-template <bool BF16, int NC>
+// CAUSAL (text tower, clip/model.py:323-329): L is the row's own limit min(L, query index + 1), and any chunk can hold
+// masked columns.
+template <bool BF16, int NC, bool CAUSAL>
 __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L, float sl2, float* s_max_b,
                                              float* s_sum_b, int half, int row, bool has_rows) {
   uint32_t r[NC][16];
@@ -48,7 +50,7 @@ __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L,
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      if (i < NC - 2) {
+      if (!CAUSAL && i < NC - 2) {
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
           m0 = fmaxf(m0, __uint_as_float(r[i][j]));
@@ -78,7 +80,7 @@ __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L,
       for (int j = 0; j < 8; ++j) {
         float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[i][2 * j]), sl2, -ms));
         float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[i][2 * j + 1]), sl2, -ms));
-        if (i >= NC - 2) {
+        if (CAUSAL || i >= NC - 2) {
           if (c * 16 + 2 * j >= L) p0 = 0.f;
           if (c * 16 + 2 * j + 1 >= L) p1 = 0.f;
         }
@@ -93,7 +95,7 @@ __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L,
   }
 }
 
-template <bool BF16, int NC>
+template <bool BF16, int NC, bool CAUSAL>
 __global__ void __launch_bounds__(P_THREADS, 1)
 attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                      uint16_t* __restrict__ out, int L, int H, int Lk, int nq, int total, int reverse) {
@@ -251,7 +253,8 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
       ptx::mbar_wait(&bar_sfull[b], k & 1);
       ptx::tc_fence_after();
-      softmax_item<BF16, NC>(t_row, c_begin, L, sl2, s_max + b * 256, s_sum + b * 256, half, row, has_rows);
+      const int lim = CAUSAL ? min(L, qt * 128 + row + 1) : L;  // valid key columns of this thread's row
+      softmax_item<BF16, NC, CAUSAL>(t_row, c_begin, lim, sl2, s_max + b * 256, s_sum + b * 256, half, row, has_rows);
       if (it > 0) {  // O(it-1): its PV was issued a whole softmax ago
         ptx::mbar_wait(bar_o, (it - 1) & 1);
         ptx::tc_fence_after();
@@ -278,7 +281,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   }
 }
 
-template <bool BF16, int NC>
+template <bool BF16, int NC, bool CAUSAL>
 cudaError_t launch_nc(const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* out, int L, int H, int Lk, int nq,
                       int total, int grid, int reverse, cudaStream_t stream) {
   static bool attr_set[64] = {};  // per device
@@ -286,23 +289,23 @@ cudaError_t launch_nc(const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* o
   cudaGetDevice(&dev);
   dev &= 63;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcp_kernel<BF16, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_tcp_kernel<BF16, NC, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  return launch_kernel(attention_tcp_kernel<BF16, NC>, grid, P_THREADS, P_SMEM, stream, 1, true, tq, tkv, out, L, H, Lk, nq,
+  return launch_kernel(attention_tcp_kernel<BF16, NC, CAUSAL>, grid, P_THREADS, P_SMEM, stream, 1, true, tq, tkv, out, L, H, Lk, nq,
                        total, reverse);
 }
 
-template <bool BF16>
+template <bool BF16, bool CAUSAL>
 cudaError_t launch_dt(int nc, const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* out, int L, int H, int Lk,
                       int nq, int total, int grid, int reverse, cudaStream_t stream) {
   switch (nc) {
-    case 3: return launch_nc<BF16, 3>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
-    case 4: return launch_nc<BF16, 4>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
-    case 5: return launch_nc<BF16, 5>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
-    case 6: return launch_nc<BF16, 6>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
-    case 7: return launch_nc<BF16, 7>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
+    case 3: return launch_nc<BF16, 3, CAUSAL>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
+    case 4: return launch_nc<BF16, 4, CAUSAL>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
+    case 5: return launch_nc<BF16, 5, CAUSAL>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
+    case 6: return launch_nc<BF16, 6, CAUSAL>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
+    case 7: return launch_nc<BF16, 7, CAUSAL>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -312,7 +315,7 @@ cudaError_t launch_dt(int nc, const CUtensorMap& tq, const CUtensorMap& tkv, uin
 bool attention_tcp_supported(int L) { return L > 64 && (L + 15) / 16 * 16 <= KV_MAX; }
 
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
-                                 int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse) {
+                                 int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse, int causal) {
   if (n_img <= 0) return cudaSuccess;
   if (!attention_tcp_supported(L)) return cudaErrorInvalidValue;
   const int Lk = (L + 15) / 16 * 16;
@@ -322,8 +325,11 @@ cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& t
   if (nq == 2) grid &= ~1;  // even: a CTA's items alternate between the full and the partial query tile
   const int nc = ((Lk >> 4) + 1) >> 1;
   uint16_t* o = static_cast<uint16_t*>(out);
-  return is_bf16 ? launch_dt<true>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream)
-                 : launch_dt<false>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream);
+  if (causal)
+    return is_bf16 ? launch_dt<true, true>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream)
+                   : launch_dt<false, true>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream);
+  return is_bf16 ? launch_dt<true, false>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream)
+                 : launch_dt<false, false>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream);
 }
 
 }  // namespace aihab

@@ -1,6 +1,7 @@
 // HBM-bound kernels of the hot path: LayerNorm, im2col, weight cast.  128-bit loads/stores, one warp per row.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include "ptx.cuh"
 
@@ -141,6 +142,55 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, int rows, int col
   }
 }
 
+// Text tower input (clip/model.py:341-342): x[row, :] = token_embedding[tokens[row], :] + positional_embedding[row % L, :]
+__global__ void __launch_bounds__(256) embed_tokens_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ emb,
+                                                           const float* __restrict__ pos, float* __restrict__ x, long rows,
+                                                           int L, int D, int vocab) {
+  const int d4 = D >> 2;
+  const long total = rows * d4;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long row = i / d4;
+    const int c = static_cast<int>(i - row * d4);
+    long tok = tokens[row];
+    tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+    const float4 e = __ldg(reinterpret_cast<const float4*>(emb + tok * D) + c);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (row % L) * D) + c);
+    reinterpret_cast<float4*>(x + row * D)[c] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+  }
+}
+
+// EOT pooling (clip/model.py:350): per sequence the row at tokens.argmax(-1) (first maximum, like torch) is copied
+// out of the residual stream; ln_final then runs on those n rows only (LayerNorm is per row, so this equals
+// ln_final(x)[arange(n), eot]).
+__global__ void __launch_bounds__(128) eot_gather_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ x,
+                                                         float* __restrict__ out, int n, int L, int D) {
+  const int seq = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (seq >= n) return;
+  long best = -0x7fffffffffffffffL - 1;
+  int bi = 0x7fffffff;
+  for (int t = lane; t < L; t += 32) {
+    const long v = tokens[static_cast<long>(seq) * L + t];
+    if (v > best || (v == best && t < bi)) {
+      best = v;
+      bi = t;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  const float4* src = reinterpret_cast<const float4*>(x + (static_cast<long>(seq) * L + bi) * D);
+  float4* dst = reinterpret_cast<float4*>(out + static_cast<long>(seq) * D);
+  for (int c = lane; c < (D >> 2); c += 32) dst[c] = src[c];
+}
+
 }  // namespace
 
 bool pdl_enabled() {
@@ -198,4 +248,22 @@ cudaError_t launch_cast_pad(const float* src, int rows, int cols, void* dst, int
   return cudaGetLastError();
 }
 
+cudaError_t launch_embed_tokens(const int64_t* tokens, const float* emb, const float* pos, float* x, long rows, int L,
+                                int D, int vocab, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if ((D & 3) != 0 || L <= 0 || vocab <= 0) return cudaErrorInvalidValue;
+  const long total = rows * (D >> 2);
+  const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 16));
+  embed_tokens_kernel<<<grid, 256, 0, stream>>>(tokens, emb, pos, x, rows, L, D, vocab);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eot_gather(const int64_t* tokens, const float* x, float* out, int n, int L, int D, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if ((D & 3) != 0) return cudaErrorInvalidValue;
+  eot_gather_kernel<<<(n + 3) / 4, 128, 0, stream>>>(tokens, x, out, n, L, D);
+  return cudaGetLastError();
+}
+
 }  // namespace aihab
+

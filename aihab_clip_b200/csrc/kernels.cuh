@@ -44,8 +44,9 @@ cudaError_t launch_attention_tc(const CUtensorMap& tmap_q, const CUtensorMap& tm
 // Persistent, software-pipelined variant (64 < L <= 224): one CTA per SM, double-buffered Q/K/V stages and S buffers,
 // epilogue of item i-1 overlapped with the PV MMA.  Same tensor maps as launch_attention_tc.
 bool attention_tcp_supported(int L);
+// causal != 0: key j is visible to query i only if j <= i (the text tower's attn_mask, clip/model.py:323-329).
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
-                                 int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse = 0);
+                                 int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse = 0, int causal = 0);
 
 // Persistent flash-style variant for long sequences (128 < L <= 1024; ViT-L/14: 257, ViT-L/14@336px: 577): keys in
 // blocks of <= 160 with an online softmax, O rescaled in TMEM only when the running max moves by more than 2^8.
@@ -87,6 +88,12 @@ cudaError_t launch_kernel(void (*kernel)(KArgs...), int grid, int block, size_t 
   cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// Text tower ends (clip/model.py:341-342, 350): embedding lookup + positional embedding into the fp32 residual stream;
+// copy of each sequence's EOT row (tokens.argmax(-1), first maximum) into out [n, D].
+cudaError_t launch_embed_tokens(const int64_t* tokens, const float* emb, const float* pos, float* x, long rows, int L,
+                                int D, int vocab, cudaStream_t stream);
+cudaError_t launch_eot_gather(const int64_t* tokens, const float* x, float* out, int n, int L, int D, cudaStream_t stream);
 
 // fp32 -> 16-bit cast of a weight matrix [rows, cols] into [rows, cols_pad] (zero padded columns).
 cudaError_t launch_cast_pad(const float* src, int rows, int cols, void* dst, int cols_pad, int out_bf16,

@@ -61,13 +61,14 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtyp
     return out
 
 
-def attention(qkv: torch.Tensor, n: int, L: int, H: int):
-    """qkv [n*L, 3*H*64] fp16/bf16 -> [n*L, H*64]."""
+def attention(qkv: torch.Tensor, n: int, L: int, H: int, causal: bool = False):
+    """qkv [n*L, 3*H*64] fp16/bf16 -> [n*L, H*64]; causal = the text tower's mask (64 < L <= 224)."""
     _need_cuda(qkv)
     assert qkv.is_contiguous() and qkv.shape == (n * L, 3 * H * 64)
     out = torch.empty(n * L, H * 64, dtype=qkv.dtype, device=qkv.device)
-    rc = _lib.load().aihab_attention(_ptr(qkv), _ptr(out), n, L, H, dtype_code(qkv.dtype), _stream(qkv.device))
-    _lib.check(rc, "aihab_attention")
+    fn = _lib.load().aihab_attention_causal if causal else _lib.load().aihab_attention
+    rc = fn(_ptr(qkv), _ptr(out), n, L, H, dtype_code(qkv.dtype), _stream(qkv.device))
+    _lib.check(rc, "aihab_attention_causal" if causal else "aihab_attention")
     return out
 
 

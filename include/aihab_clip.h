@@ -86,6 +86,26 @@ typedef struct {
   const aihab_vit_block_weights* blocks; /* [layers], host array */
 } aihab_vit_weights;
 
+/* Text tower: CLIP.encode_text (clip/model.py:338-353) on the same GEMM / LayerNorm / attention
+ * kernels with the causal mask of build_attention_mask (:323-329).  heads = width / 64. */
+typedef struct aihab_text aihab_text;
+typedef struct {
+  int context_length; /* 77; 65..224 supported (persistent tcgen05 attention) */
+  int vocab_size;     /* 49408 */
+  int width;          /* transformer_width, multiple of 128 */
+  int layers;
+  int heads;          /* width / 64 */
+  int dtype;          /* AIHAB_F16 or AIHAB_BF16 */
+  int max_batch;      /* prompts per internal chunk */
+} aihab_text_config;
+typedef struct {
+  const float* token_embedding;      /* [vocab, width] */
+  const float* positional_embedding; /* [context_length, width] */
+  const float* ln_final_weight;      /* [width] */
+  const float* ln_final_bias;        /* [width] */
+  const aihab_vit_block_weights* blocks; /* transformer.resblocks.{i}.*, [layers], host array */
+} aihab_text_weights;
+
 /* Library / device ------------------------------------------------------------------------------------- */
 AIHAB_API int aihab_abi_version(void);
 AIHAB_API const char* aihab_last_error(void);
@@ -155,6 +175,14 @@ AIHAB_API int aihab_score16(const void* feats16, int n, int D, int dtype, const 
                             int C, float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx,
                             float* topk_val, void* stream);
 
+/* Text tower: create / destroy as for the image tower.  aihab_text_encode replaces the transformer part of
+ * CLIP.encode_text (clip/model.py:341-350): tokens [n, context_length] int64 on the device ->
+ * feats_out [n, width] = ln_final(x)[arange(n), tokens.argmax(-1)], i.e. the reference's x_before_proj
+ * (the caller applies @ text_projection, :351).  n may exceed max_batch. */
+AIHAB_API int aihab_text_create(const aihab_text_config* cfg, const aihab_text_weights* w, int device, aihab_text** out);
+AIHAB_API void aihab_text_destroy(aihab_text* h);
+AIHAB_API int aihab_text_encode(aihab_text* h, const int64_t* tokens, int n, void* feats_out, int out_dtype, void* stream);
+
 /* Metrics epilogue after the logits, one launch (aihab_utils/evaluation.py): aggregate_logits_to_l2 (:92-142,
  * reduce 0 = sum, 1 = mean, 2 = logsumexp, accumulated in L3-id order like the reference loop), the top-k over the
  * L2 logits that L2MetricsAccumulator.update takes (:186-221), and top3_metrics (:261-273): top-3 indices of the L3
@@ -174,6 +202,8 @@ AIHAB_API int aihab_layernorm(const float* x, int rows, int D, const float* gamm
                     void* out16, int out16_dtype, void* stream);
 /* softmax(q k^T / 8) v per (image, head); qkv [n*L, 3*H*64] 16-bit -> out [n*L, H*64]. */
 AIHAB_API int aihab_attention(const void* qkv, void* out, int n, int L, int H, int dtype, void* stream);
+/* Same with the text tower's causal mask (key j visible to query i only for j <= i); 64 < L <= 224. */
+AIHAB_API int aihab_attention_causal(const void* qkv, void* out, int n, int L, int H, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

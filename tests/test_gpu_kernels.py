@@ -147,6 +147,24 @@ def test_attention_online_rescale(cuda_device, dtype, L, H, n):
     np.testing.assert_allclose(out, ref, atol=eps * 4, rtol=eps * 3)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("L,H,n", [(77, 8, 5), (65, 1, 3), (128, 2, 2), (224, 2, 2), (100, 12, 7)])
+def test_attention_causal(cuda_device, dtype, L, H, n):
+    """The text tower's mask (clip/model.py:323-329: -inf above the diagonal): key j visible to query i for j <= i."""
+    _lib, ops = _ops()
+    rng = np.random.default_rng(L * 3 + H)
+    D = H * 64
+    qkv = _rand16(rng, (n * L, 3 * D), 1.5, dtype)
+    out = ops.attention(qkv.to(cuda_device), n, L, H, causal=True).float().cpu().numpy()
+    q, k, v = (t.reshape(n, L, H, 64).transpose(0, 2, 1, 3) for t in np.split(qkv.double().numpy(), 3, axis=-1))
+    s = q @ k.transpose(0, 1, 3, 2) / 8.0
+    s = np.where(np.tril(np.ones((L, L), dtype=bool)), s, -np.inf)
+    p = np.exp(s - s.max(-1, keepdims=True))
+    ref = ((p / p.sum(-1, keepdims=True)) @ v).transpose(0, 2, 1, 3).reshape(n * L, D)
+    eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    np.testing.assert_allclose(out, ref, atol=eps * 3, rtol=eps * 2)
+
+
 def test_preprocess_bit_exact(cuda_device, gold, meta):
     _lib, ops = _ops()
     from aihab_clip_b200.weights import synthetic_images_u8

@@ -191,3 +191,49 @@ def test_vit_l_geometries_match_oracle(tmp_path, cuda_device, geom_name, n):
     ref = O.encode_image(make_state_dict_np(geom, 3, with_text=False), ref_x)
     assert cosine(feats, ref).min() >= 0.999
     np.testing.assert_allclose(feats, ref, atol=1e-2, rtol=0)
+
+
+def test_text_tower_on_tensor_cores_matches_reference_golden(tmp_path, cuda_device, gold):
+    """text_engine='b200' (SURVEY 8f row 3): CLIP.encode_text (clip/model.py:338-353) on libaihab_clip.so with the
+    causal mask, against the goldens of the unmodified reference (ViT-B/32 text tower: width 512, 8 heads, 12 layers,
+    77 tokens) and against the PyTorch text tower of the same model."""
+    from aihab_clip_b200 import _lib
+    geom, seed, _ = case_images("b32")
+    _, model, _ = load_model(tmp_path, geom.name, seed, cuda_device)
+    model.float()
+    tok = torch.from_numpy(gold["b32_tok"]).to(cuda_device)
+    ref_before, ref_emb = gold["b32_text_before"], gold["b32_text_emb"]
+    with torch.no_grad():
+        tb, te = model.encode_text(tok)  # default: PyTorch fp32
+    np.testing.assert_allclose(tb.cpu().numpy(), ref_before, atol=2e-4, rtol=0)
+    n0 = _lib.kernel_launches()
+    model.text_engine = "b200"
+    model.text_max_batch = 2  # 3 prompts -> 2 chunks
+    xb, xe = model.encode_text(tok)
+    xe = xe.detach()
+    assert _lib.kernel_launches() - n0 >= 2 * (12 * 5 + 3)
+    assert xb.dtype == torch.float32 and tuple(xb.shape) == ref_before.shape and tuple(xe.shape) == ref_emb.shape
+    b = xb.cpu().numpy()
+    assert np.isfinite(b).all()
+    assert cosine(b, ref_before).min() >= 0.9995
+    np.testing.assert_allclose(b, ref_before, atol=2e-2, rtol=0)  # ln_final output is O(1); fp16 operands
+    assert cosine(xe.cpu().numpy(), ref_emb).min() >= 0.9995
+    # the class head built from it (utils.py:45-54) and the x100 logits it produces on unit-norm image embeddings
+    w_ref = O.text_head([ref_emb[i:i + 1] for i in range(ref_emb.shape[0])])
+    w_gpu = O.text_head([xe.cpu().numpy()[i:i + 1] for i in range(ref_emb.shape[0])])
+    assert cosine(w_gpu.T, w_ref.T).min() >= 0.9995
+    rng = np.random.default_rng(3)
+    img = rng.standard_normal((256, w_ref.shape[0])).astype(np.float32)
+    img /= np.linalg.norm(img, axis=1, keepdims=True)
+    assert np.abs(100.0 * img @ w_gpu - 100.0 * img @ w_ref).max() <= 5e-2
+    # the reference's own class head (clip_classifier over the 20 shipped class prompts, one template)
+    _, ce = model.encode_text(torch.from_numpy(gold["b32_texts"]).to(cuda_device))
+    w20 = torch.nn.functional.normalize(ce.detach(), dim=-1).t().cpu().numpy()
+    assert cosine(w20.T, gold["b32_text_w"].T).min() >= 0.9995
+    assert np.abs(100.0 * img @ w20 - 100.0 * img @ gold["b32_text_w"]).max() <= 5e-2
+    # chunking does not change a prompt's result
+    model.text_max_batch = 512
+    xb2, _ = model.encode_text(tok)
+    assert torch.equal(xb, xb2)
+    with pytest.raises(RuntimeError):
+        model.encode_text(tok.cpu())

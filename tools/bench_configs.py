@@ -99,6 +99,21 @@ def main():
                  "ms_per_step": round(ms, 3), "rows_per_s": round(n / ms * 1e3), "gbs_algorithmic": round(algo / ms / 1e6, 1),
                  "frac_of_hbm_peak": round(algo / ms / 1e6 / peaks["hbm"], 3),
                  "torch_formulation_ms": round(ms_t, 3)})
+    # text tower for a prompt ensemble (20 classes x 80 templates = 1600 prompts, 77 tokens)
+    geom = GEOMETRIES["ViT-B/16"]
+    model = build_model(make_state_dict(geom, 0)).to(dev).float()
+    tok = torch.randint(1, 49000, (1600, 77), device=dev)
+    tok[:, 0] = 49406
+    tok[torch.arange(1600), torch.randint(8, 77, (1600,), device=dev)] = 49407  # EOT = highest id
+    flops = 1600 * (12 * 77 * 2 * 12 * 512 * 512 + 12 * 4 * 77 * 77 * 512)
+    with torch.no_grad():
+        ms_t = time_steps(lambda: model.encode_text(tok), 3, warm=1)
+        model.text_engine = "b200"
+        model.text_max_batch = model.visual.preferred_batch(dev, 512) if False else 492  # 492 x 77 rows = 148 tile pairs
+        ms = time_steps(lambda: model.encode_text(tok), 5, warm=2)
+    rows.append({"config": "text tower (width 512, 12 layers, causal) 1600 prompts x 77 tokens, text_engine=b200",
+                 "ms_per_step": round(ms, 3), "prompts_per_s": round(1600 / ms * 1e3), "tflops": round(flops / ms / 1e9, 1),
+                 "frac_of_tensor_peak": round(flops / ms / 1e9 / peaks["tensor"], 3), "torch_fp32_ms": round(ms_t, 3)})
     for r in rows:
         print(json.dumps(r))
 
