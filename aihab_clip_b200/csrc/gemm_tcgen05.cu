@@ -16,9 +16,9 @@ constexpr int EPI_WARP0 = 4;  // warps 4.. are the epilogue (warp % 4 selects th
 __host__ __device__ constexpr bool epi_out16(int epi) {
   return epi == EPI_BIAS_16 || epi == EPI_BIAS_GELU_16 || epi == EPI_LN_BIAS_16 || epi == EPI_LN_BIAS_GELU_16;
 }
-// 16-bit-output epilogues do the activation math (bias / LayerNorm fold / QuickGELU): two warps per TMEM lane quadrant
-// (8 epilogue warps, 384 threads) so they keep up with the MMA; the fp32 epilogues are memory-bound: one warp each.
-__host__ __device__ constexpr int epi_warps(int epi) { return epi_out16(epi) ? 8 : 4; }
+// Two warps per TMEM lane quadrant (8 epilogue warps, 384 threads) so the epilogue keeps up with the MMA; the fp32
+// residual epilogue streams 4 KB TMA boxes instead: one warp per quadrant.
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == EPI_BIAS_RES_32 ? 4 : 8; }
 __host__ __device__ constexpr int num_threads(int epi) { return (EPI_WARP0 + epi_warps(epi)) * 32; }
 
 constexpr int RS = 4;           // residual ring slots per epilogue warp (EPI_BIAS_RES_32)
@@ -33,10 +33,10 @@ struct SmemLayout {
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr bool kOut16 = epi_out16(EPI);
   static constexpr int kStages =
-      TWO ? (kRes ? 4 : (kOut16 ? 5 : 6)) : ((BN == 256) ? ((kRes || kOut16) ? 3 : 4) : (kRes ? 4 : (kOut16 ? 5 : 6)));
+      TWO ? (kRes ? 4 : 5) : ((BN == 256) ? 3 : (kRes ? 4 : 5));
   static constexpr int kStageBytes = kABytes + kBBytes;
   // residual ring (4 warps x RS boxes) + 4 x 2 KB for the coalesced gamma*x store | 8 or 4 warps x 4 KB staging tile
-  static constexpr int kStagingBytes = kRes ? 4 * RS * RES_BOX + 4 * 2048 : (kOut16 ? 8 * 4096 : 4 * 4096);
+  static constexpr int kStagingBytes = kRes ? 4 * RS * RES_BOX + 4 * 2048 : 8 * 4096;
   static constexpr int kBiasBytes = 4 * BN * 4;  // [2][BN] bias + [2][BN] auxiliary per-column vector (s_n / gamma)
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kStages * kABytes;
@@ -225,7 +225,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr int kEpiThreads = epi_warps(EPI) * 32;
     const int ew = warp & 3;                   // TMEM lanes [32*ew, 32*ew+32) (hardware: warp % 4)
     const int ehalf = (warp - EPI_WARP0) >> 2;  // 0, or 0/1 when two warps share a quadrant
-    uint8_t* stg = sStaging + (kOut16 ? (warp - EPI_WARP0) * 4096 : ew * 4096);
+    uint8_t* stg = sStaging + (L::kRes ? ew : warp - EPI_WARP0) * 4096;
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..kEpiThreads-1
     const bool bf16 = p.ab_format != 0;
     // EPI_BIAS_RES_32: every warp streams its 32-row slice of the fp32 residual through a private ring of 4 KB
@@ -444,8 +444,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               make_float2(ln_s1, ln_s2);
         }
       } else {
+        // EPI_PATCH_32: the 8 rows this lane stores are the same for every chunk of the tile - patch row -> token row
+        // (one class-token row per image is skipped) and its positional-embedding row are resolved once per tile
+        int tok_row[8], pos_row[8];
+        if constexpr (EPI == EPI_PATCH_32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int grow = m0 + i * 4 + (lane >> 3);
+            const int img = grow / p.g2;
+            pos_row[i] = 1 + grow - img * p.g2;
+            tok_row[i] = img * (p.g2 + 1) + pos_row[i];
+          }
+        }
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = ehalf; c < BN / 32; c += 2) {  // 32-column chunks dealt alternately to the quadrant's two warps
           uint32_t r[32];
           ptx::tmem_ld_32x32(taddr + c * 32, r);
           ptx::tmem_ld_wait();
@@ -487,15 +499,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 v.w += x.w;
                 *dst = v;
               } else if constexpr (EPI == EPI_PATCH_32) {
-                const int img = grow / p.g2;
-                const int pi = grow - img * p.g2;
-                const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pi) * p.N + gcol));
+                const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(pos_row[i]) * p.N + gcol));
                 v.x += pe.x;
                 v.y += pe.y;
                 v.z += pe.z;
                 v.w += pe.w;
-                const size_t tok = static_cast<size_t>(img) * (p.g2 + 1) + 1 + pi;
-                *reinterpret_cast<float4*>(p.out32 + tok * p.ldo + gcol) = v;
+                *reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(tok_row[i]) * p.ldo + gcol) = v;
               } else {
                 *reinterpret_cast<float4*>(p.out32 + static_cast<size_t>(grow) * p.ldo + gcol) = v;
               }
