@@ -5,12 +5,18 @@
 //   accumulate fp32 in TMEM; epilogue variants cover every GEMM site of the reference hot path
 //   (clip/model.py:171-175,181,184-185,217-221 ; methods/ProLIP.py:40 ; methods/utils.py:185).
 //
-// Roles (256 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
-//   warp 0 (one lane)  TMA producer : cp.async.bulk.tensor 128x64 A box + BNx64 W box per stage, SWIZZLE_128B
-//   warp 1 (one lane)  MMA issuer   : 4 x tcgen05.mma (M=128, N=BN, K=16) per stage, tcgen05.commit -> barriers
-//   warp 2             TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4..7         epilogue     : tcgen05.ld -> bias/activation in fp32 -> smem transpose -> 128 B coalesced
-//                                     row segments to global (optionally read-modify-write of the fp32 residual)
+// Roles (384 threads, 256 for the residual epilogue; 1 CTA / SM, persistent, static round-robin tile schedule;
+// CTA pairs = clusters of 2 with tcgen05 cta_group::2 and UMMA M = 256 when wave quantisation allows):
+//   warp 0 (one lane)  TMA producer : cp.async.bulk.tensor 128x64 A box + BNx64 W box (half of it per CTA of a pair)
+//                                     per stage, SWIZZLE_128B, 3-5 stage mbarrier ring
+//   warp 1 (one lane)  MMA issuer   : 4 x tcgen05.mma (M=128|256, N=BN, K=16) per stage, tcgen05.commit -> barriers
+//   warp 2             TMEM allocator (2 accumulator stages x BN fp32 columns: epilogue of tile i overlaps MMAs of i+1)
+//   warps 4..11        epilogue     : tcgen05.ld -> bias / LayerNorm fold / QuickGELU in fp32 -> swizzled smem staging
+//                                     -> TMA store (16-bit outputs) or 128 B row segments (fp32 outputs);
+//                      warps 4..7 only for EPI_BIAS_RES_32: fp32 residual read-modify-write through a ring of 4 KB
+//                                     TMA boxes, LayerNorm statistics + gamma * x for the next GEMM
+// Every kernel calls griddepcontrol.launch_dependents at entry and griddepcontrol.wait before its first global access
+// (programmatic dependent launch along the stream).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
