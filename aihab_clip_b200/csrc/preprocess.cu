@@ -102,57 +102,74 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   }
 }
 
-// Fast path when the input already has the crop size (new == in, Pillow skips both passes): one thread converts 16
-// consecutive pixels of one image row (48 contiguous input bytes, 3 x 128-bit loads) into three 32-byte runs of the
-// im2col row (one per channel).  Requires p % 16 == 0 (ViT-B/16, ViT-B/32) so a run never straddles a patch.
+// ToTensor + Normalize of one uint8: (x / 255 - mean) / std with both divisions correctly rounded, as torchvision's
+// fp32 tensor ops evaluate it, but without the division sequence: q = a * RN(1/b), r = fma(-b, q, a), q' = fma(r, RN(1/b), q)
+// is the correctly rounded quotient (Markstein); checked exhaustively for the 256 x 3 possible inputs against IEEE
+// division (and covered by the bit-exact preprocessing tests).
+__device__ __forceinline__ float normalize_u8(uint32_t x, float mean, float stdv, float rstd) {
+  const float xf = static_cast<float>(x);
+  const float r255 = 1.0f / 255.0f;
+  float q = __fmul_rn(xf, r255);
+  const float t = __fmaf_rn(__fmaf_rn(-255.0f, q, xf), r255, q);
+  const float num = __fsub_rn(t, mean);
+  q = __fmul_rn(num, rstd);
+  return __fmaf_rn(__fmaf_rn(-stdv, q, num), rstd, q);
+}
+
+// Fast path when the input already has the crop size (new == in, Pillow skips both passes) and the im2col rows have no
+// K padding: one CTA converts one strip of p image rows (one row of patches).  The strip is staged in smem with
+// coalesced 128-bit loads; a thread turns 8 consecutive pixels (24 bytes, three 64-bit smem loads) into one 16-byte
+// chunk per channel; the strip's im2col output (g patches x 3 p^2 elements) is ONE contiguous block and every warp
+// store covers 512 contiguous bytes.  Requires p % 8 == 0.
 template <bool BF16>
-__global__ void __launch_bounds__(256) normalize_im2col16_kernel(const uint8_t* __restrict__ in, int n, int sh, int sw,
-                                                                 int R, int top, int left, uint16_t* __restrict__ out,
-                                                                 int p, int Kpad) {
-  const int segs = R >> 4;
-  const long total = static_cast<long>(n) * R * segs;
-  const int g = R / p;
+__global__ void __launch_bounds__(256) normalize_im2col16_kernel(const uint8_t* __restrict__ in, int sh, int sw, int R,
+                                                                 int top, int left, uint16_t* __restrict__ out, int p) {
+  extern __shared__ __align__(16) uint8_t strip[];  // [p][R * 3]
+  const int gy = blockIdx.x, img = blockIdx.y;
+  const int g = R / p, RC = R * 3;
+  const uint8_t* src0 = in + ((static_cast<size_t>(img) * sh + top + gy * p) * sw + left) * 3;
+  const size_t row_pitch = static_cast<size_t>(sw) * 3;
+  if (((reinterpret_cast<uintptr_t>(src0) | row_pitch | static_cast<size_t>(RC)) & 15) == 0) {
+    const int vec_per_row = RC >> 4;
+    for (int i = threadIdx.x; i < p * vec_per_row; i += blockDim.x) {
+      const int r = i / vec_per_row, v = i - r * vec_per_row;
+      reinterpret_cast<uint4*>(strip + r * RC)[v] = __ldg(reinterpret_cast<const uint4*>(src0 + r * row_pitch) + v);
+    }
+  } else {
+    for (int i = threadIdx.x; i < p * RC; i += blockDim.x) {
+      const int r = i / RC;
+      strip[i] = __ldg(src0 + r * row_pitch + (i - r * RC));
+    }
+  }
+  __syncthreads();
   const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
   const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int xs = static_cast<int>(idx % segs);
-    const long t = idx / segs;
-    const int y = static_cast<int>(t % R);
-    const int img = static_cast<int>(t / R);
-    const uint8_t* src = in + ((static_cast<size_t>(img) * sh + top + y) * sw + left + xs * 16) * 3;
-    uint32_t w[12];  // 48 bytes = 16 RGB pixels
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+  const float rstd[3] = {1.0f / 0.26862954f, 1.0f / 0.26130258f, 1.0f / 0.27577711f};
+  const int kx8n = p >> 3;              // 8-pixel groups per patch row
+  const int groups = g * p * kx8n;      // 8-pixel groups of the strip
+  uint16_t* dst0 = out + (static_cast<size_t>(img) * g + gy) * g * 3 * p * p;
+  for (int q = threadIdx.x; q < groups; q += blockDim.x) {
+    const int kx8 = q % kx8n;
+    const int t = q / kx8n;
+    const int ky = t % p;
+    const int gx = t / p;
+    uint32_t w[6];  // 24 bytes = 8 RGB pixels; RC and 24 * k are multiples of 8
+    const uint2* px = reinterpret_cast<const uint2*>(strip + ky * RC + (gx * p + kx8 * 8) * 3);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
-        w[4 * i] = v.x;
-        w[4 * i + 1] = v.y;
-        w[4 * i + 2] = v.z;
-        w[4 * i + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 12; ++i)
-        w[i] = __ldg(src + 4 * i) | (__ldg(src + 4 * i + 1) << 8) | (__ldg(src + 4 * i + 2) << 16) |
-               (static_cast<uint32_t>(__ldg(src + 4 * i + 3)) << 24);
+    for (int i = 0; i < 3; ++i) {
+      const uint2 v = px[i];
+      w[2 * i] = v.x;
+      w[2 * i + 1] = v.y;
     }
-    auto px = [&](int i) { return static_cast<float>((w[i >> 2] >> ((i & 3) * 8)) & 0xffu); };
-    const int x0 = xs * 16;
-    const int gy = y / p, ky = y - gy * p, gx = x0 / p, kx = x0 - gx * p;
-    uint16_t* dst = out + (static_cast<size_t>(img) * g * g + gy * g + gx) * Kpad + ky * p + kx;
+    auto byte_at = [&](int i) { return (w[i >> 2] >> ((i & 3) * 8)) & 0xffu; };
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      uint32_t pk[8];
+      uint32_t pk[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float a = (px((2 * j) * 3 + c) / 255.0f - mean[c]) / stdv[c];
-        const float b = (px((2 * j + 1) * 3 + c) / 255.0f - mean[c]) / stdv[c];
-        pk[j] = ptx::pack2<BF16>(a, b);
-      }
-      uint4* d = reinterpret_cast<uint4*>(dst + c * p * p);
-      d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      for (int j = 0; j < 4; ++j)
+        pk[j] = ptx::pack2<BF16>(normalize_u8(byte_at(6 * j + c), mean[c], stdv[c], rstd[c]),
+                                 normalize_u8(byte_at(6 * j + 3 + c), mean[c], stdv[c], rstd[c]));
+      *reinterpret_cast<uint4*>(dst0 + (gx * 3 + c) * p * p + ky * p + kx8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
@@ -198,16 +215,16 @@ cudaError_t launch_preprocess(const uint8_t* in, int n, int sh, int sw, int R, c
     max_rows = TH * scale_up + t.v_ksize + 2;
     if (max_rows > sh) max_rows = sh;
   }
-  if (layout == 1 && !t.need_h && !t.need_v && (p % 16) == 0 && (R % 16) == 0 && Kpad == 3 * p * p &&
-      out_dtype != 0) {
-    const long total = static_cast<long>(n) * R * (R / 16);
-    const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 16));
+  if (layout == 1 && !t.need_h && !t.need_v && (p % 8) == 0 && (R % p) == 0 && (R % 8) == 0 && Kpad == 3 * p * p &&
+      out_dtype != 0 && p * R * 3 <= 40 * 1024) {
+    const dim3 grid(R / p, n);
+    const size_t smem = static_cast<size_t>(p) * R * 3;
     if (out_dtype == 2)
-      normalize_im2col16_kernel<true><<<grid, 256, 0, stream>>>(in, n, sh, sw, R, t.crop_top, t.crop_left,
-                                                                static_cast<uint16_t*>(out), p, Kpad);
+      normalize_im2col16_kernel<true><<<grid, 256, smem, stream>>>(in, sh, sw, R, t.crop_top, t.crop_left,
+                                                                   static_cast<uint16_t*>(out), p);
     else
-      normalize_im2col16_kernel<false><<<grid, 256, 0, stream>>>(in, n, sh, sw, R, t.crop_top, t.crop_left,
-                                                                 static_cast<uint16_t*>(out), p, Kpad);
+      normalize_im2col16_kernel<false><<<grid, 256, smem, stream>>>(in, sh, sw, R, t.crop_top, t.crop_left,
+                                                                    static_cast<uint16_t*>(out), p);
     return cudaGetLastError();
   }
   if (layout == 1 && Kpad > 3 * p * p) {
