@@ -1041,6 +1041,32 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
   return 0;
 }
 
+int aihab_prototype_scores(const float* emb, const int64_t* labels, int n, int E, const float* prototypes_t,
+                           const int64_t* owner, int P, float* sim_to_prototype, int64_t* prototype_id,
+                           float* sim_to_other, float* margin, void* stream) {
+  if (n < 0 || E <= 0 || P <= 0) return fail("aihab_prototype_scores: bad argument");
+  if (n == 0) return 0;
+  if (emb == nullptr || labels == nullptr || prototypes_t == nullptr || owner == nullptr || sim_to_prototype == nullptr)
+    return fail("aihab_prototype_scores: null buffer");
+  const int dev = device_of(emb);
+  DeviceGuard guard(dev);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  keep_pool_warm(dev);
+  const int chunk = 65536;  // rows per pass: the [rows, P] similarity tile stays small
+  float* sim = nullptr;
+  CK(cudaMallocAsync(&sim, static_cast<size_t>(std::min(n, chunk)) * P * 4, s));
+  ProfScope ps(PC_SCORE, 2.0 * n * static_cast<double>(E) * P, s);
+  for (int i0 = 0; i0 < n; i0 += chunk) {
+    const int nb = std::min(chunk, n - i0);
+    CKL(aihab::launch_sgemm(emb + static_cast<size_t>(i0) * E, prototypes_t, sim, nb, P, E, 1.0f, s));
+    CKL(aihab::launch_prototype_reduce(sim, labels + i0, owner, nb, P, sim_to_prototype + i0,
+                                       prototype_id ? prototype_id + i0 : nullptr, sim_to_other ? sim_to_other + i0 : nullptr,
+                                       margin ? margin + i0 : nullptr, s));
+  }
+  CK(cudaFreeAsync(sim, s));
+  return 0;
+}
+
 int aihab_l2_metrics(const float* logits_l3, int n, int C3, const int32_t* l3_to_l2, int C2, int reduce, int k,
                      float* logits_l2_out, int64_t* topk_idx, float* topk_val, int64_t* top3_idx, float* top3_prob,
                      void* stream) {

@@ -122,6 +122,11 @@ cudaError_t launch_l2_metrics(const float* logits_l3, int n, int C3, const int* 
                               float* logits_l2_out, int64_t* topk_idx, float* topk_val, int64_t* top3_idx,
                               float* top3_prob, cudaStream_t stream);
 
+// masked row maxima of a similarity matrix sim [n, P] against prototype owners (tools/outlier_cleaning.py:553-668)
+cudaError_t launch_prototype_reduce(const float* sim, const int64_t* labels, const int64_t* owner, int n, int P,
+                                    float* sim_own, int64_t* proto_id, float* sim_other, float* margin,
+                                    cudaStream_t stream);
+
 // tensor-core scoring helpers (aihab_score16): 16-bit transpose, fp16 hi/lo splits of the text weights and of the
 // normalised embedding (A' = e_hi | e_hi | e_lo against W' = w_hi | w_lo | w_hi reproduces the fp32 product to ~2^-21)
 cudaError_t launch_transpose16(const void* src, void* dst, int R, int Cc, cudaStream_t stream);

@@ -512,6 +512,53 @@ __global__ void __launch_bounds__(128) l2_metrics_small_kernel(const float* __re
   }
 }
 
+// ---- multi-prototype scoring over cached embeddings (tools/outlier_cleaning.py:553-668): per row of the similarity
+// matrix sim [n, P] = emb @ prototypes^T: the best similarity among the prototypes of the row's own class (and that
+// prototype's index inside its class block, first maximum), the best among all other classes (NaN if there is none)
+// and the margin between the two.  owner[p] = class of prototype p; class blocks are contiguous.  One warp per row.
+__global__ void __launch_bounds__(128) prototype_reduce_kernel(const float* __restrict__ sim, const int64_t* __restrict__ labels,
+                                                               const int64_t* __restrict__ owner, int n, int P,
+                                                               float* __restrict__ sim_own, int64_t* __restrict__ proto_id,
+                                                               float* __restrict__ sim_other, float* __restrict__ margin) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* src = sim + static_cast<size_t>(row) * P;
+  const int64_t lab = labels[row];
+  float bv = -INFINITY, ov = -INFINITY;
+  int bi = 0x7fffffff, first_own = 0x7fffffff;
+  for (int p = lane; p < P; p += 32) {
+    const float v = src[p];
+    if (owner[p] == lab) {
+      first_own = min(first_own, p);
+      if (precedes(v, p, bv, bi)) {
+        bv = v;
+        bi = p;
+      }
+    } else {
+      ov = fmaxf(ov, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float tv = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int ti = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (precedes(tv, ti, bv, bi)) {
+      bv = tv;
+      bi = ti;
+    }
+    ov = fmaxf(ov, __shfl_xor_sync(0xffffffffu, ov, o));
+    first_own = min(first_own, __shfl_xor_sync(0xffffffffu, first_own, o));
+  }
+  if (lane == 0) {
+    const float other = isinf(ov) ? __int_as_float(0x7fc00000) : ov;  // masked_fill(isinf, nan)
+    sim_own[row] = bv;
+    if (proto_id != nullptr) proto_id[row] = bi == 0x7fffffff ? -1 : bi - first_own;
+    if (sim_other != nullptr) sim_other[row] = other;
+    if (margin != nullptr) margin[row] = bv - other;
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_transpose16(const void* src, void* dst, int R, int Cc, cudaStream_t stream) {
@@ -591,6 +638,14 @@ cudaError_t launch_l2_metrics(const float* logits_l3, int n, int C3, const int* 
   const size_t smem = (static_cast<size_t>(C3) + 4 * (C3 + C2)) * sizeof(float);
   l2_metrics_kernel<<<(n + 3) / 4, 128, smem, stream>>>(logits_l3, n, C3, l3_to_l2, C2, reduce, k, logits_l2_out, topk_idx,
                                                         topk_val, top3_idx, top3_prob);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prototype_reduce(const float* sim, const int64_t* labels, const int64_t* owner, int n, int P,
+                                    float* sim_own, int64_t* proto_id, float* sim_other, float* margin,
+                                    cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  prototype_reduce_kernel<<<(n + 3) / 4, 128, 0, stream>>>(sim, labels, owner, n, P, sim_own, proto_id, sim_other, margin);
   return cudaGetLastError();
 }
 

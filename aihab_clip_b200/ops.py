@@ -155,3 +155,24 @@ def l2_metrics(logits_l3: torch.Tensor, l3_to_l2, num_l2: int, reduce: str = "me
                                       _ptr(val), _ptr(t3i), _ptr(t3p), _stream(dev))
     _lib.check(rc, "aihab_l2_metrics")
     return out, idx, val, t3i, t3p
+
+
+def prototype_scores(emb: torch.Tensor, labels: torch.Tensor, prototypes: torch.Tensor, owner: torch.Tensor):
+    """tools/outlier_cleaning.py:553-668 on CUDA tensors: emb [n, E] L2-normalised, labels [n], prototypes [P, E]
+    (class blocks contiguous), owner [P] class id per prototype.  Returns (sim_to_prototype [n], prototype_id [n]
+    index inside the class block, sim_to_other_class_best [n] (NaN without another class), margin [n])."""
+    _need_cuda(emb, labels, prototypes, owner)
+    e = emb.float().contiguous()
+    n, E = e.shape
+    pt = prototypes.to(device=e.device, dtype=torch.float32).t().contiguous()  # [E, P]
+    P = pt.shape[1]
+    lab = labels.to(device=e.device, dtype=torch.int64).contiguous()
+    own = owner.to(device=e.device, dtype=torch.int64).contiguous()
+    sim = torch.empty(n, dtype=torch.float32, device=e.device)
+    pid = torch.empty(n, dtype=torch.int64, device=e.device)
+    oth = torch.empty(n, dtype=torch.float32, device=e.device)
+    mar = torch.empty(n, dtype=torch.float32, device=e.device)
+    rc = _lib.load().aihab_prototype_scores(_ptr(e), _ptr(lab), n, E, _ptr(pt), _ptr(own), P, _ptr(sim), _ptr(pid),
+                                            _ptr(oth), _ptr(mar), _stream(e.device))
+    _lib.check(rc, "aihab_prototype_scores")
+    return sim, pid, oth, mar

@@ -193,6 +193,16 @@ AIHAB_API int aihab_l2_metrics(const float* logits_l3, int n, int C3, const int3
                                float* logits_l2_out, int64_t* topk_idx, float* topk_val, int64_t* top3_idx,
                                float* top3_prob, void* stream);
 
+/* Multi-prototype / centroid scoring over cached embeddings (tools/outlier_cleaning.py:553-668; with one prototype
+ * per class it is the centroid similarity of :296-337): sim = emb @ prototypes^T in fp32, then per row the best
+ * similarity among the prototypes of its own class (prototype_id = index inside the class block, first maximum), the
+ * best among all other classes (NaN when there is no other class) and margin = own - other.
+ *   emb [n,E] fp32 L2-normalised, labels [n] int64, prototypes_t [E,P] fp32 (TRANSPOSED, class blocks contiguous),
+ *   owner [P] int64 = class id of each prototype.  prototype_id / sim_to_other / margin may be null. */
+AIHAB_API int aihab_prototype_scores(const float* emb, const int64_t* labels, int n, int E, const float* prototypes_t,
+                                     const int64_t* owner, int P, float* sim_to_prototype, int64_t* prototype_id,
+                                     float* sim_to_other, float* margin, void* stream);
+
 /* Building blocks (exported for per-kernel parity tests; same kernels the tower uses) ---------------------- */
 /* D[M,N] = A[M,K] * W[N,K]^T with a fused epilogue; A, W 16-bit (ab_dtype), K % 8 == 0. */
 AIHAB_API int aihab_gemm16(const void* A, const void* W, int M, int N, int K, int ab_dtype, int epilogue, const float* bias,

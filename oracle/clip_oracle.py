@@ -193,6 +193,26 @@ def top3_metrics(outputs: np.ndarray, labels: np.ndarray):
     return correct, idx, top3
 
 
+def prototype_scores(emb: np.ndarray, labels: np.ndarray, prototypes: np.ndarray, owner: np.ndarray):
+    """tools/outlier_cleaning.py:553-668 (MultiPrototypeScorer.score_prototype_distance, tensor part) — cosine
+    similarity of L2-normalised embeddings to the nearest prototype of their own class (index inside the class block,
+    first maximum), best similarity to any other class's prototype (NaN if there is none) and the margin.  With one
+    prototype per class it is SingleCentroidScorer.score_centroid_distance (:296-337).
+    prototypes [P, E] with class blocks contiguous, owner [P] = class id of each prototype."""
+    emb = np.asarray(emb, dtype=np.float32)
+    sim = emb @ np.asarray(prototypes, dtype=np.float32).T
+    labels = np.asarray(labels)
+    owner = np.asarray(owner)
+    same = owner[None, :] == labels[:, None]
+    own = np.where(same, sim, -np.inf)
+    best = own.argmax(axis=1)                      # first maximum
+    sim_own = own[np.arange(len(labels)), best]
+    first = np.array([np.flatnonzero(owner == c)[0] for c in labels])
+    other = np.where(same, -np.inf, sim).max(axis=1)
+    other = np.where(np.isinf(other), np.nan, other).astype(np.float32)
+    return sim_own.astype(np.float32), (best - first).astype(np.int64), other, (sim_own - other).astype(np.float32)
+
+
 def cls_acc(output: np.ndarray, target: np.ndarray, topk: int = 1) -> float:
     """methods/utils.py:16-21 — top-k accuracy in percent."""
     pred = topk_indices(output, topk)

@@ -305,3 +305,39 @@ def test_evaluation_mirrors_use_the_fused_kernel_on_cuda(cuda_device):
     assert int(c_cpu) == int(c_gpu) and torch.equal(i_cpu, i_gpu.cpu())
     torch.testing.assert_close(p_gpu.cpu(), p_cpu, rtol=3e-6, atol=1e-9)
     assert _lib.kernel_launches() > n0  # the CUDA calls went through libaihab_clip.so
+
+
+def test_prototype_scores_match_reference_golden(cuda_device):
+    """aihab_prototype_scores against the unmodified reference's outputs and the oracle."""
+    from pathlib import Path
+    _lib, ops = _ops()
+    g = np.load(Path(__file__).resolve().parent / "golden" / "prototype_scores.npz")
+    t = lambda k: torch.from_numpy(g[k]).to(cuda_device)
+    sim, pid, other, margin = ops.prototype_scores(t("emb"), t("labels"), t("prototypes"), t("owner"))
+    np.testing.assert_allclose(sim.cpu().numpy(), g["sim_to_prototype"], atol=2e-6, rtol=0)
+    np.testing.assert_array_equal(pid.cpu().numpy(), g["prototype_id"])
+    np.testing.assert_allclose(other.cpu().numpy(), g["sim_to_other_class_best"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(margin.cpu().numpy(), g["margin_to_other_class"], atol=4e-6, rtol=0)
+    sim_c, pid_c, _, _ = ops.prototype_scores(t("emb"), t("labels"), t("centroids"), t("centroid_owner"))
+    np.testing.assert_allclose(sim_c.cpu().numpy(), g["sim_to_centroid"], atol=2e-6, rtol=0)
+    assert int(pid_c.abs().sum()) == 0
+    # larger than one chunk of rows, many prototypes, single-class NaN rule: against the oracle
+    rng = np.random.default_rng(9)
+    n, E, P = 70000, 512, 96
+    emb = rng.standard_normal((n, E)).astype(np.float32)
+    emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    protos = rng.standard_normal((P, E)).astype(np.float32)
+    protos /= np.linalg.norm(protos, axis=1, keepdims=True)
+    owner = np.sort(rng.integers(0, 20, P)).astype(np.int64)
+    labels = rng.choice(np.unique(owner), n).astype(np.int64)
+    got = ops.prototype_scores(*(torch.from_numpy(a).to(cuda_device) for a in (emb, labels, protos, owner)))
+    ref = O.prototype_scores(emb, labels, protos, owner)
+    np.testing.assert_allclose(got[0].cpu().numpy(), ref[0], atol=3e-6, rtol=0)
+    tied = np.abs(got[0].cpu().numpy() - ref[0]) > 0  # index must agree unless two prototypes are within rounding
+    assert (got[1].cpu().numpy() == ref[1]).mean() > 0.9999
+    np.testing.assert_allclose(got[2].cpu().numpy(), ref[2], atol=3e-6, rtol=0)
+    np.testing.assert_allclose(got[3].cpu().numpy(), ref[3], atol=6e-6, rtol=0)
+    one = owner == owner[0]
+    o1 = ops.prototype_scores(torch.from_numpy(emb[:100]).to(cuda_device), torch.full((100,), int(owner[0]), device=cuda_device),
+                              torch.from_numpy(protos[one]).to(cuda_device), torch.from_numpy(owner[one]).to(cuda_device))
+    assert torch.isnan(o1[2]).all() and torch.isnan(o1[3]).all()

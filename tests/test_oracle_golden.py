@@ -116,3 +116,24 @@ def test_agreement_set_subset_matches_oracle(gold):
     _, logits, _ = O.score(O.encode_image(sd, x), sd["visual.proj"], gold["b32_text_w"], 100.0, 1)
     ref = np.concatenate([gold["agree_logits"][:16], gold["agree_logits"][n // 2:n // 2 + 16]])
     np.testing.assert_allclose(logits, ref, atol=1e-3, rtol=0)
+
+
+def test_prototype_scores_match_reference_golden():
+    """oracle.prototype_scores against tools/outlier_cleaning.py of the unmodified reference
+    (tests/golden/make_golden_prototypes.py -> prototype_scores.npz)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "prototype_scores.npz")
+    sim, pid, other, margin = O.prototype_scores(g["emb"], g["labels"], g["prototypes"], g["owner"])
+    np.testing.assert_allclose(sim, g["sim_to_prototype"], atol=2e-6, rtol=0)
+    np.testing.assert_array_equal(pid, g["prototype_id"])
+    np.testing.assert_allclose(other, g["sim_to_other_class_best"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(margin, g["margin_to_other_class"], atol=4e-6, rtol=0)
+    # one prototype per class = the single-centroid scorer
+    sim_c, pid_c, _, _ = O.prototype_scores(g["emb"], g["labels"], g["centroids"], g["centroid_owner"])
+    np.testing.assert_allclose(sim_c, g["sim_to_centroid"], atol=2e-6, rtol=0)
+    assert (pid_c == 0).all()
+    # a single class has no "other" class: NaN like the reference
+    one = g["labels"] == g["labels"][0]
+    _, _, o1, m1 = O.prototype_scores(g["emb"][one], g["labels"][one], g["prototypes"][g["owner"] == g["labels"][0]],
+                                      g["owner"][g["owner"] == g["labels"][0]])
+    assert np.isnan(o1).all() and np.isnan(m1).all()

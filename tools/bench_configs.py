@@ -99,6 +99,24 @@ def main():
                  "ms_per_step": round(ms, 3), "rows_per_s": round(n / ms * 1e3), "gbs_algorithmic": round(algo / ms / 1e6, 1),
                  "frac_of_hbm_peak": round(algo / ms / 1e6 / peaks["hbm"], 3),
                  "torch_formulation_ms": round(ms_t, 3)})
+    # multi-prototype scoring over cached embeddings (tools/outlier_cleaning.py:553-668)
+    emb = torch.nn.functional.normalize(torch.randn(n, 512, device=dev), dim=1)
+    protos = torch.nn.functional.normalize(torch.randn(96, 512, device=dev), dim=1)
+    owner = torch.sort(torch.randint(0, 20, (96,), device=dev)).values
+    plab = owner[torch.randint(0, 96, (n,), device=dev)]
+    ms = time_steps(lambda: ops.prototype_scores(emb, plab, protos, owner), 5, warm=2)
+
+    def torch_protos():
+        sim_all = emb @ protos.t()
+        same = owner.unsqueeze(0) == plab.unsqueeze(1)
+        sim_all.masked_fill(~same, float("-inf")).max(dim=1)
+        sim_all.masked_fill(same, float("-inf")).max(dim=1)
+
+    ms_t = time_steps(torch_protos, 3, warm=1)
+    rows.append({"config": f"prototype scoring {n} x 512 embeddings vs 96 prototypes of 20 classes (fp32 sgemm + masked row maxima)",
+                 "ms_per_step": round(ms, 3), "rows_per_s": round(n / ms * 1e3), "tflops_fp32": round(2.0 * n * 512 * 96 / ms / 1e9, 1),
+                 "torch_formulation_ms": round(ms_t, 3)})
+    del emb
     # text tower for a prompt ensemble (20 classes x 80 templates = 1600 prompts, 77 tokens)
     geom = GEOMETRIES["ViT-B/16"]
     model = build_model(make_state_dict(geom, 0)).to(dev).float()
