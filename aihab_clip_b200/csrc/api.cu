@@ -1053,17 +1053,50 @@ int aihab_prototype_scores(const float* emb, const int64_t* labels, int n, int E
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   keep_pool_warm(dev);
   const int chunk = 65536;  // rows per pass: the [rows, P] similarity tile stays small
+  const int rows_tmp = std::min(n, chunk);
   float* sim = nullptr;
-  CK(cudaMallocAsync(&sim, static_cast<size_t>(std::min(n, chunk)) * P * 4, s));
+  CK(cudaMallocAsync(&sim, static_cast<size_t>(rows_tmp) * P * 4, s));
   ProfScope ps(PC_SCORE, 2.0 * n * static_cast<double>(E) * P, s);
+  const bool tensor = (E % 8) == 0 && (P % 4) == 0;
+  void *a3 = nullptr, *w3 = nullptr;
+  const int sms = sm_count(dev);
+  if (tensor) {
+    // sim = e_hi p_hi + e_hi p_lo + e_lo p_hi as ONE K = 3E fp16 tcgen05 GEMM with fp32 accumulation (relative error
+    // ~2^-21, the hi/lo split of aihab_score16) instead of an fp32 CUDA-core GEMM
+    CK(aihab::gemm_init());
+    CK(cudaMallocAsync(&a3, static_cast<size_t>(rows_tmp) * 3 * E * 2, s));
+    CK(cudaMallocAsync(&w3, static_cast<size_t>(P) * 3 * E * 2, s));
+    CKL(aihab::launch_split_textw(prototypes_t, E, P, w3, s));  // [E, P] fp32 -> [P, 3E] fp16 (hi | lo | hi)
+  }
   for (int i0 = 0; i0 < n; i0 += chunk) {
     const int nb = std::min(chunk, n - i0);
-    CKL(aihab::launch_sgemm(emb + static_cast<size_t>(i0) * E, prototypes_t, sim, nb, P, E, 1.0f, s));
-    CKL(aihab::launch_prototype_reduce(sim, labels + i0, owner, nb, P, sim_to_prototype + i0,
+    const float* e = emb + static_cast<size_t>(i0) * E;
+    if (tensor) {
+      CKL(aihab::launch_l2norm_split(e, nullptr, a3, nb, E, s, /*normalize=*/0));
+      aihab::GemmParams p{};
+      CUtensorMap ma, mw;
+      const int bn = aihab::gemm_block_n(nb, P, sms);
+      CK(aihab::make_tmap_2d_16bit(&ma, a3, nb, 3 * E, static_cast<uint64_t>(3 * E) * 2, 128, 0));
+      CK(aihab::make_tmap_2d_16bit(&mw, w3, P, 3 * E, static_cast<uint64_t>(3 * E) * 2, bn, 0));
+      p.M = nb;
+      p.N = P;
+      p.K = 3 * E;
+      p.ab_format = 0;
+      p.epilogue = aihab::EPI_SCALE_32;
+      p.out32 = sim;
+      p.ldo = P;
+      p.scale = 1.0f;
+      CKL(aihab::launch_gemm(ma, mw, nullptr, p, bn, sms, s));
+    } else {
+      CKL(aihab::launch_sgemm(e, prototypes_t, sim, nb, P, E, 1.0f, s));
+    }
+    CKL(aihab::launch_prototype_reduce(sim, labels + i0, owner, nb, P, P, sim_to_prototype + i0,
                                        prototype_id ? prototype_id + i0 : nullptr, sim_to_other ? sim_to_other + i0 : nullptr,
                                        margin ? margin + i0 : nullptr, s));
   }
   CK(cudaFreeAsync(sim, s));
+  if (a3) CK(cudaFreeAsync(a3, s));
+  if (w3) CK(cudaFreeAsync(w3, s));
   return 0;
 }
 

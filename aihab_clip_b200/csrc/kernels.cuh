@@ -123,7 +123,7 @@ cudaError_t launch_l2_metrics(const float* logits_l3, int n, int C3, const int* 
                               float* top3_prob, cudaStream_t stream);
 
 // masked row maxima of a similarity matrix sim [n, P] against prototype owners (tools/outlier_cleaning.py:553-668)
-cudaError_t launch_prototype_reduce(const float* sim, const int64_t* labels, const int64_t* owner, int n, int P,
+cudaError_t launch_prototype_reduce(const float* sim, const int64_t* labels, const int64_t* owner, int n, int P, int ld,
                                     float* sim_own, int64_t* proto_id, float* sim_other, float* margin,
                                     cudaStream_t stream);
 
@@ -131,7 +131,8 @@ cudaError_t launch_prototype_reduce(const float* sim, const int64_t* labels, con
 // normalised embedding (A' = e_hi | e_hi | e_lo against W' = w_hi | w_lo | w_hi reproduces the fp32 product to ~2^-21)
 cudaError_t launch_transpose16(const void* src, void* dst, int R, int Cc, cudaStream_t stream);
 cudaError_t launch_split_textw(const float* w, int E, int C, void* out, cudaStream_t stream);
-cudaError_t launch_l2norm_split(const float* emb, float* emb_out, void* a3, int rows, int E, cudaStream_t stream);
+cudaError_t launch_l2norm_split(const float* emb, float* emb_out, void* a3, int rows, int E, cudaStream_t stream,
+                                int normalize = 1);
 
 // ---- preprocessing (data/clip_transforms.py:50-56; Pillow ImagingResample fixed-point bicubic)
 struct ResampleTables {

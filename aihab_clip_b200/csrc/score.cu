@@ -308,21 +308,25 @@ __global__ void split_textw_kernel(const float* __restrict__ w, int E, int C, ui
   }
 }
 
-// rows of emb fp32 [rows, E]: L2-normalise (F.normalize eps) -> optional fp32 copy + A' [rows, 3E] fp16 (hi | hi | lo)
+// rows of emb fp32 [rows, E]: L2-normalise (F.normalize eps; skipped when normalize == 0: the rows are used as they
+// are) -> optional fp32 copy + A' [rows, 3E] fp16 (hi | hi | lo)
 __global__ void __launch_bounds__(128) l2norm_split_kernel(const float* __restrict__ emb, float* __restrict__ emb_out,
-                                                           uint16_t* __restrict__ a3, int rows, int E) {
+                                                           uint16_t* __restrict__ a3, int rows, int E, int normalize) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* src = emb + static_cast<size_t>(row) * E;
-  float s = 0.f;
-  for (int c = lane; c < E; c += 32) s = fmaf(src[c], src[c], s);
+  float denom = 1.0f;
+  if (normalize) {
+    float s = 0.f;
+    for (int c = lane; c < E; c += 32) s = fmaf(src[c], src[c], s);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float denom = fmaxf(sqrtf(s), 1e-12f);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    denom = fmaxf(sqrtf(s), 1e-12f);
+  }
   uint16_t* dst = a3 + static_cast<size_t>(row) * 3 * E;
   for (int c = lane; c < E; c += 32) {
-    const float v = src[c] / denom;
+    const float v = normalize ? src[c] / denom : src[c];
     if (emb_out != nullptr) emb_out[static_cast<size_t>(row) * E + c] = v;
     uint16_t hi, lo;
     split_hi_lo(v, hi, lo);
@@ -518,12 +522,12 @@ __global__ void __launch_bounds__(128) l2_metrics_small_kernel(const float* __re
 // and the margin between the two.  owner[p] = class of prototype p; class blocks are contiguous.  One warp per row.
 __global__ void __launch_bounds__(128) prototype_reduce_kernel(const float* __restrict__ sim, const int64_t* __restrict__ labels,
                                                                const int64_t* __restrict__ owner, int n, int P,
-                                                               float* __restrict__ sim_own, int64_t* __restrict__ proto_id,
+                                                               int ld, float* __restrict__ sim_own, int64_t* __restrict__ proto_id,
                                                                float* __restrict__ sim_other, float* __restrict__ margin) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
-  const float* src = sim + static_cast<size_t>(row) * P;
+  const float* src = sim + static_cast<size_t>(row) * ld;
   const int64_t lab = labels[row];
   float bv = -INFINITY, ov = -INFINITY;
   int bi = 0x7fffffff, first_own = 0x7fffffff;
@@ -574,9 +578,10 @@ cudaError_t launch_split_textw(const float* w, int E, int C, void* out, cudaStre
   return cudaGetLastError();
 }
 
-cudaError_t launch_l2norm_split(const float* emb, float* emb_out, void* a3, int rows, int E, cudaStream_t stream) {
+cudaError_t launch_l2norm_split(const float* emb, float* emb_out, void* a3, int rows, int E, cudaStream_t stream,
+                                int normalize) {
   if (rows <= 0) return cudaSuccess;
-  l2norm_split_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(emb, emb_out, static_cast<uint16_t*>(a3), rows, E);
+  l2norm_split_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(emb, emb_out, static_cast<uint16_t*>(a3), rows, E, normalize);
   return cudaGetLastError();
 }
 
@@ -641,11 +646,11 @@ cudaError_t launch_l2_metrics(const float* logits_l3, int n, int C3, const int* 
   return cudaGetLastError();
 }
 
-cudaError_t launch_prototype_reduce(const float* sim, const int64_t* labels, const int64_t* owner, int n, int P,
+cudaError_t launch_prototype_reduce(const float* sim, const int64_t* labels, const int64_t* owner, int n, int P, int ld,
                                     float* sim_own, int64_t* proto_id, float* sim_other, float* margin,
                                     cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  prototype_reduce_kernel<<<(n + 3) / 4, 128, 0, stream>>>(sim, labels, owner, n, P, sim_own, proto_id, sim_other, margin);
+  prototype_reduce_kernel<<<(n + 3) / 4, 128, 0, stream>>>(sim, labels, owner, n, P, ld, sim_own, proto_id, sim_other, margin);
   return cudaGetLastError();
 }
 

@@ -113,8 +113,8 @@ def main():
         sim_all.masked_fill(same, float("-inf")).max(dim=1)
 
     ms_t = time_steps(torch_protos, 3, warm=1)
-    rows.append({"config": f"prototype scoring {n} x 512 embeddings vs 96 prototypes of 20 classes (fp32 sgemm + masked row maxima)",
-                 "ms_per_step": round(ms, 3), "rows_per_s": round(n / ms * 1e3), "tflops_fp32": round(2.0 * n * 512 * 96 / ms / 1e9, 1),
+    rows.append({"config": f"prototype scoring {n} x 512 embeddings vs 96 prototypes of 20 classes (tcgen05 hi/lo-split GEMM + masked row maxima)",
+                 "ms_per_step": round(ms, 3), "rows_per_s": round(n / ms * 1e3), "tflops_algorithmic": round(2.0 * n * 512 * 96 / ms / 1e9, 1),
                  "torch_formulation_ms": round(ms_t, 3)})
     del emb
     # text tower for a prompt ensemble (20 classes x 80 templates = 1600 prompts, 77 tokens)
