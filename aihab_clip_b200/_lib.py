@@ -49,6 +49,8 @@ SIGNATURES = {
     "aihab_last_error": (C.c_char_p, []),
     "aihab_kernel_launches": (C.c_uint64, []),
     "aihab_profile_enable": (C.c_int, [C.c_int]),
+    "aihab_profile_sites": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_uint64), C.c_int]),
     "aihab_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_int]),
     "aihab_vit_create": (C.c_int, [C.POINTER(VitConfig), C.POINTER(VitWeights), C.c_int, C.POINTER(C.c_void_p)]),
     "aihab_vit_destroy": (None, [C.c_void_p]),
@@ -115,6 +117,16 @@ PROFILE_CLASSES = {"gemm": 0, "attention": 1, "layernorm": 2, "preprocess": 3, "
 
 def profile_enable(on: bool) -> None:
     load().aihab_profile_enable(1 if on else 0)
+
+
+def profile_sites(cls: str, cap: int = 16) -> list:
+    """[{'work': algorithmic FLOPs or bytes per launch, 'tag': site tag (GEMM: N), 'ms': summed event time,
+    'launches': n}] per launch site of a kernel class.  Non-resetting: call before profile_read(reset=True)."""
+    work, tag, ms, n = (C.c_double * cap)(), (C.c_int * cap)(), (C.c_double * cap)(), (C.c_uint64 * cap)()
+    g = load().aihab_profile_sites(PROFILE_CLASSES[cls], work, tag, ms, n, cap)
+    if g < 0:
+        check(1, "aihab_profile_sites")
+    return [{"work": work[i], "tag": int(tag[i]), "ms": ms[i], "launches": int(n[i])} for i in range(g)]
 
 
 def profile_read(cls: str, reset: bool = True) -> dict:

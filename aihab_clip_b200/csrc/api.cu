@@ -30,6 +30,7 @@ struct ProfRec {
   cudaEvent_t a, b;
   int cls;
   double work;
+  int aux;  // site tag within a class (GEMM: N)
 };
 std::mutex g_prof_mu;
 bool g_prof_on = false;
@@ -40,7 +41,7 @@ struct ProfScope {
   bool on = false;
   ProfRec r{};
   cudaStream_t s;
-  ProfScope(int cls, double work, cudaStream_t stream) : s(stream) {
+  ProfScope(int cls, double work, cudaStream_t stream, int aux = 0) : s(stream) {
     if (!g_prof_on) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (!g_prof_free.empty()) {
@@ -53,6 +54,7 @@ struct ProfScope {
     }
     r.cls = cls;
     r.work = work;
+    r.aux = aux;
     on = true;
     cudaEventRecord(r.a, s);
   }
@@ -424,9 +426,9 @@ int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], in
   p.scale = 1.0f;
   p.reverse_m = reverse;
   const int bn = aihab::gemm_block_n(M, N, h->num_sms);
-  if (n_blocks_out) *n_blocks_out = (N + bn - 1) / bn;
+  if (n_blocks_out) *n_blocks_out = (N + 127) / 128;  // LayerNorm statistics: one partial per row and 128 columns
   const bool pair = gemm_pair_enabled(M, N, h->num_sms);  // a pair stages the 256-wide W tile as two 128-row halves
-  ProfScope ps(PC_GEMM, 2.0 * M * N * K, s);
+  ProfScope ps(PC_GEMM, 2.0 * M * N * K, s, N);
   CKL(aihab::launch_gemm(ma, mw[(bn == 256 && !pair) ? 1 : 0], epi == aihab::EPI_BIAS_RES_32 ? &h->m_x : nullptr, p, bn,
                          h->num_sms, s, pair));
   return 0;
@@ -660,6 +662,36 @@ int aihab_profile_read(int cls, double* ms_out, uint64_t* launches_out, double* 
   if (launches_out) *launches_out = cnt;
   if (work_out) *work_out = work;
   return 0;
+}
+
+int aihab_profile_sites(int cls, double* work_out, int* aux_out, double* ms_out, uint64_t* launches_out, int cap) {
+  if (cls < 0 || cls >= PC_COUNT || cap < 0) {
+    fail("aihab_profile_sites: bad argument");
+    return -1;
+  }
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (const ProfRec& r : g_prof_recs) {
+    if (r.cls != cls) continue;
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) {
+      fail("aihab_profile_sites: event query failed");
+      return -1;
+    }
+    int g = 0;
+    while (g < n && (work_out[g] != r.work || aux_out[g] != r.aux)) ++g;
+    if (g == n) {
+      if (n == cap) continue;  // more distinct sites than the caller asked for: the rest are dropped
+      work_out[n] = r.work;
+      aux_out[n] = r.aux;
+      ms_out[n] = 0.0;
+      launches_out[n] = 0;
+      ++n;
+    }
+    ms_out[g] += t;
+    launches_out[g] += 1;
+  }
+  return n;
 }
 
 int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, int device, aihab_vit** out) {

@@ -13,16 +13,27 @@ constexpr int BM = 128;      // UMMA M (one CTA, cta_group::1): accumulator row 
 constexpr int BK = 64;       // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;   // fixed for 16-bit operands
 constexpr int EPI_WARP0 = 4;  // warps 4.. are the epilogue (warp % 4 selects the TMEM lane quadrant)
-__host__ __device__ constexpr bool epi_out16(int epi) {
-  return epi == EPI_BIAS_16 || epi == EPI_BIAS_GELU_16 || epi == EPI_LN_BIAS_16 || epi == EPI_LN_BIAS_GELU_16;
+// Two warps per TMEM lane quadrant (8 epilogue warps, 384 threads) so the epilogue keeps up with the MMA.  The fp32
+// residual epilogue streams 4 KB TMA boxes through per-warp rings, one warp per quadrant.  -DAIHAB_RES_WARPS_PAIR=8
+// runs it on two warps per quadrant in CTA pairs (each owns one 128-column half of the tile; operand stages / ring
+// slots via AIHAB_RES_STAGES_PAIR / AIHAB_RES_RS_PAIR): measured on B200 it is no faster (out_proj 0.0747 -> 0.0759 ms
+// hot, step unchanged) - in the step these GEMMs wait for DRAM, not for the epilogue warps - so the default stays 4.
+#ifndef AIHAB_RES_WARPS_PAIR
+#define AIHAB_RES_WARPS_PAIR 4
+#endif
+#ifndef AIHAB_RES_STAGES_PAIR
+#define AIHAB_RES_STAGES_PAIR 4
+#endif
+#ifndef AIHAB_RES_RS_PAIR
+#define AIHAB_RES_RS_PAIR 2
+#endif
+__host__ __device__ constexpr int epi_warps(int epi, bool two) {
+  return epi == EPI_BIAS_RES_32 ? (two ? AIHAB_RES_WARPS_PAIR : 4) : 8;
 }
-// Two warps per TMEM lane quadrant (8 epilogue warps, 384 threads) so the epilogue keeps up with the MMA; the fp32
-// residual epilogue streams 4 KB TMA boxes instead: one warp per quadrant.
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == EPI_BIAS_RES_32 ? 4 : 8; }
-__host__ __device__ constexpr int num_threads(int epi) { return (EPI_WARP0 + epi_warps(epi)) * 32; }
+__host__ __device__ constexpr int num_threads(int epi, bool two) { return (EPI_WARP0 + epi_warps(epi, two)) * 32; }
 
-constexpr int RS = 4;           // residual ring slots per epilogue warp (EPI_BIAS_RES_32)
 constexpr int RES_BOX = 32 * 128;  // 32 rows x 32 fp32 = 4 KB TMA box, SWIZZLE_128B
+constexpr int STAT_COLS = 128;     // LayerNorm producer: one (sum, sum of squares) partial per row and 128 columns
 
 template <int BN, int EPI, bool TWO>
 struct SmemLayout {
@@ -31,19 +42,20 @@ struct SmemLayout {
   // read-modify-write, not by the MMA pipe.  In a CTA pair each CTA stages only half of the W tile.
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
-  static constexpr bool kOut16 = epi_out16(EPI);
+  static constexpr int kResWarps = epi_warps(EPI_BIAS_RES_32, TWO);  // residual epilogue warps (rings)
+  static constexpr int kRS = (TWO && kResWarps == 8) ? AIHAB_RES_RS_PAIR : 4;  // ring slots per residual epilogue warp
   static constexpr int kStages =
-      TWO ? (kRes ? 4 : 5) : ((BN == 256) ? 3 : (kRes ? 4 : 5));
+      TWO ? (kRes ? (kResWarps == 8 ? AIHAB_RES_STAGES_PAIR : 4) : 5) : ((BN == 256) ? 3 : (kRes ? 4 : 5));
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // residual ring (4 warps x RS boxes) + 4 x 2 KB for the coalesced gamma*x store | 8 or 4 warps x 4 KB staging tile
-  static constexpr int kStagingBytes = kRes ? 4 * RS * RES_BOX + 4 * 2048 : 8 * 4096;
+  // residual rings (kResWarps x kRS boxes) + 2 KB per warp for the coalesced gamma*x store | 8 warps x 4 KB staging tile
+  static constexpr int kStagingBytes = kRes ? kResWarps * (kRS * RES_BOX + 2048) : 8 * 4096;
   static constexpr int kBiasBytes = 4 * BN * 4;  // [2][BN] bias + [2][BN] auxiliary per-column vector (s_n / gamma)
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kStages * kABytes;
   static constexpr int kOffStaging = kStages * kStageBytes;
   static constexpr int kOffBias = kOffStaging + kStagingBytes;
   static constexpr int kOffBars = kOffBias + kBiasBytes;
-  static constexpr int kNumBars = 2 * kStages + 4 + 4 * RS;
+  static constexpr int kNumBars = 2 * kStages + 4 + 8 * 4;
   static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemSlot + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
@@ -70,7 +82,7 @@ __device__ __forceinline__ float quick_gelu(float x) {
 // 128 A rows and HALF of the W tile (the pair's MMA reads both halves), owns the accumulator rows of its A rows and
 // runs its own epilogue.  Halves the W shared-memory fill and L2 -> SM traffic per FLOP.
 template <int BN, int EPI, bool TWO>
-__global__ void __launch_bounds__(num_threads(EPI), 1)
+__global__ void __launch_bounds__(num_threads(EPI, TWO), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   using L = SmemLayout<BN, EPI, TWO>;
@@ -89,7 +101,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* res_full_bar = tmem_empty_bar + 2;  // [4 epilogue warps][RS]
+  uint64_t* res_full_bar = tmem_empty_bar + 2;  // [residual epilogue warps][RS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
 
   const int warp = threadIdx.x >> 5;
@@ -121,9 +133,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
-      ptx::mbar_init(&tmem_empty_bar[i], epi_warps(EPI) * (TWO ? 2 : 1));  // one arrive per epilogue warp (of the pair)
+      ptx::mbar_init(&tmem_empty_bar[i], epi_warps(EPI, TWO) * (TWO ? 2 : 1));  // one arrive per epilogue warp (of the pair)
     }
-    for (int i = 0; i < 4 * RS; ++i) ptx::mbar_init(&res_full_bar[i], 1);
+    for (int i = 0; i < L::kResWarps * L::kRS; ++i) ptx::mbar_init(&res_full_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -222,19 +234,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------ epilogue
-    constexpr int kEpiThreads = epi_warps(EPI) * 32;
+    constexpr int kEpiThreads = epi_warps(EPI, TWO) * 32;
     const int ew = warp & 3;                   // TMEM lanes [32*ew, 32*ew+32) (hardware: warp % 4)
     const int ehalf = (warp - EPI_WARP0) >> 2;  // 0, or 0/1 when two warps share a quadrant
-    uint8_t* stg = sStaging + (L::kRes ? ew : warp - EPI_WARP0) * 4096;
+    uint8_t* stg = sStaging + (warp - EPI_WARP0) * 4096;  // 16-bit / plain fp32 epilogues (not the residual rings)
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..kEpiThreads-1
     const bool bf16 = p.ab_format != 0;
     // EPI_BIAS_RES_32: every warp streams its 32-row slice of the fp32 residual through a private ring of 4 KB
     // TMA boxes (load -> add in place -> TMA store), prefetching RS-1 boxes ahead across tile boundaries.
-    constexpr int CPT = BN / 32;  // residual boxes per tile per warp
-    uint64_t* my_full = res_full_bar + ew * RS;
-    uint8_t* my_ring = sStaging + ew * (RS * RES_BOX);
+    constexpr int RS = L::kRS;
+    constexpr int CPT = BN / 32 / (L::kResWarps / 4);  // residual boxes per tile per warp: a run of CPT * 32 columns
+    const int er = warp - EPI_WARP0;                   // ring of this warp (= ew + 4 * ehalf)
+    const int c_off = ehalf * CPT;                     // first 32-column chunk of the tile owned by this warp
+    uint64_t* my_full = res_full_bar + er * RS;
+    uint8_t* my_ring = sStaging + er * (RS * RES_BOX);
     auto res_prefetch = [&](int q) {  // lane 0 only: issue the TMA load of this warp's q-th box, if it exists
-      const int itq = q / CPT, cq = q - itq * CPT;
+      const int itq = q / CPT, cq = c_off + (q - itq * CPT);
       const long tq = static_cast<long>(unit) + static_cast<long>(itq) * num_units;
       if (tq >= num_tiles) return;
       const int mb = tile_m(static_cast<int>(tq));
@@ -380,7 +395,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         float ln_s1 = 0.f, ln_s2 = 0.f;  // LayerNorm producer: this row's sum / sum of squares over the tile
         const int prow = m0 + lane;
 #pragma unroll 1
-        for (int c = 0; c < CPT; ++c, ++q) {
+        for (int cl = 0; cl < CPT; ++cl, ++q) {
+          const int c = c_off + cl;
           const int slot = q % RS;
           uint32_t r[32];
           ptx::tmem_ld_32x32(taddr + c * 32, r);
@@ -411,7 +427,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
           for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(box + lane * 128 + ((u ^ (lane & 7)) << 4)) = xv[u];
           if (ln_prod) {  // gamma * x_new: transpose through smem so each store covers 8 complete 64 B row segments
-            uint8_t* ast = sStaging + 4 * RS * RES_BOX + ew * 2048;
+            uint8_t* ast = sStaging + L::kResWarps * (RS * RES_BOX) + er * 2048;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               *reinterpret_cast<uint4*>(ast + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) =
@@ -438,10 +454,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             res_prefetch(q + RS - 1);   // ... which is exactly the slot box q+RS-1 lands in
           }
           __syncwarp();
-        }
-        if (ln_prod && prow < p.M) {
-          *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(prow) * n_blocks + n_blk) * 2) =
-              make_float2(ln_s1, ln_s2);
+          // one partial per row and STAT_COLS columns, whatever the tile width or the number of epilogue warps: the
+          // consumer adds the N / STAT_COLS partials of a row in order, so the statistics (and with them every
+          // per-image result) do not depend on the launch configuration the batch size selects
+          if (ln_prod && (c & (STAT_COLS / 32 - 1)) == STAT_COLS / 32 - 1) {
+            const int sblk = (n0 + c * 32) / STAT_COLS;
+            if (prow < p.M && sblk * STAT_COLS < p.N)
+              *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(prow) * ((p.N + STAT_COLS - 1) / STAT_COLS) + sblk) * 2) =
+                  make_float2(ln_s1, ln_s2);
+            ln_s1 = ln_s2 = 0.f;
+          }
         }
       } else {
         // EPI_PATCH_32: the 8 rows this lane stores are the same for every chunk of the tile - patch row -> token row
@@ -554,10 +576,10 @@ cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
                        int grid, bool pair, cudaStream_t stream) {
   if constexpr (BN == 256) {
     if (pair)  // CTA pairs: cluster of 2, grid = 2 x #pairs
-      return launch_kernel(gemm_kernel<256, EPI, true>, grid, num_threads(EPI), SmemLayout<256, EPI, true>::kDynamic,
+      return launch_kernel(gemm_kernel<256, EPI, true>, grid, num_threads(EPI, true), SmemLayout<256, EPI, true>::kDynamic,
                            stream, 2, true, ta, tw, tc, p);
   }
-  return launch_kernel(gemm_kernel<BN, EPI, false>, grid, num_threads(EPI), SmemLayout<BN, EPI, false>::kDynamic, stream,
+  return launch_kernel(gemm_kernel<BN, EPI, false>, grid, num_threads(EPI, false), SmemLayout<BN, EPI, false>::kDynamic, stream,
                        1, true, ta, tw, tc, p);
 }
 

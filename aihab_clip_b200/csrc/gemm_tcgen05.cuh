@@ -52,7 +52,8 @@ struct GemmParams {
   int debug;          // 0 = normal; 77 = skip the 16-bit epilogues entirely (main-loop ceiling measurement, AIHAB_GEMM_DEBUG)
   // EPI_BIAS_RES_32 as LayerNorm PRODUCER (optional, ln_gamma != nullptr): besides updating the residual it stores
   //   a16_out[m,n] = round16(ln_gamma[n] * x_new[m,n])            (A operand of the next GEMM, ld = N)
-  //   stats_out[m, n_blk, 0..1] = (sum, sum of squares) of x_new over this tile's columns (deterministic order)
+  //   stats_out[m, n / 128, 0..1] = (sum, sum of squares) of x_new over 128-column blocks (deterministic order,
+  //   independent of tile width and warp layout)
   const float* ln_gamma;
   void* a16_out;
   float* stats_out;

@@ -275,7 +275,9 @@ def run_b200(args):
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         n_launch = _lib.kernel_launches() - n0
         _lib.profile_enable(False)
+        sites_ = _lib.profile_sites("gemm") if per_launch_events else []
         prof_ = {c: _lib.profile_read(c, reset=True) for c in _lib.PROFILE_CLASSES}
+        prof_["gemm"]["sites"] = sites_
         return float(t_ms.item()), n_launch, prof_
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -329,6 +331,17 @@ def run_b200(args):
             else:
                 kernels[c] = {"share_of_step": r["ms"] / ms_prof, "launches": r["launches"], "gbs": rate / 1e9,
                               "frac_of_hbm_peak": rate / 1e9 / peaks["hbm"]}
+        if g.get("sites"):
+            # one entry per GEMM shape of the step (work per launch = 2*M*N*K identifies the site)
+            M_tok, Dw, pp = B * geom.tokens, geom.vision_width, geom.vision_patch_size
+            names = {(2.0 * M_tok * 3 * Dw * Dw, 3 * Dw): "qkv", (2.0 * M_tok * Dw * Dw, Dw): "out_proj",
+                     (2.0 * M_tok * 4 * Dw * Dw, 4 * Dw): "c_fc", (2.0 * M_tok * 4 * Dw * Dw, Dw): "c_proj",
+                     (2.0 * B * geom.grid ** 2 * Dw * (-(-3 * pp * pp // 64) * 64), Dw): "patch_embed"}
+            kernels["gemm"]["sites"] = {
+                names.get((sr["work"], sr["tag"]), "N=%d work=%.4g" % (sr["tag"], sr["work"])): {
+                    "launches": sr["launches"], "avg_ms": sr["ms"] / sr["launches"],
+                    "tflops": sr["work"] * sr["launches"] / (sr["ms"] * 1e-3) / 1e12}
+                for sr in g["sites"] if sr["ms"] > 0}
         total_tflops = value / world * flops_per_image(geom, args.classes) / 1e12
         # CPU baseline on a bounded sample (rank 0, N = 1 only)
         cpu = None

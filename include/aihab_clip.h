@@ -118,6 +118,11 @@ AIHAB_API uint64_t aihab_kernel_launches(void);
  * recorded since the last reset; it synchronises on the recorded events. */
 AIHAB_API int aihab_profile_enable(int on);
 AIHAB_API int aihab_profile_read(int cls, double* ms, uint64_t* launches, double* work, int reset);
+/* Per launch site: groups the records of class `cls` by (algorithmic work per launch, site tag; for a GEMM 2*M*N*K and
+ * N, so one group per GEMM shape of the step) and writes work per launch, tag, summed milliseconds and launch count of
+ * up to `cap` groups.  Returns the number of groups, -1 on error.  Does not reset; call it before
+ * aihab_profile_read(reset). */
+AIHAB_API int aihab_profile_sites(int cls, double* work_per_launch, int* tag, double* ms, uint64_t* launches, int cap);
 
 /* Image tower -------------------------------------------------------------------------------------------
  * Replaces build_model(...).visual construction + convert_weights (clip/model.py:372-433): packs the weights
