@@ -103,35 +103,27 @@ def cpu_text_head(sd_np, n_classes: int, embed_dim: int) -> np.ndarray:
     return w / np.linalg.norm(w, axis=0, keepdims=True)
 
 
-def cpu_reference_pass(geom, sd_np, text_w, images_u8):
-    """The reference's CPU fp32 path for this workload, restated in oracle/ (numpy, all host BLAS threads)."""
-    from oracle import clip_oracle as O
-    x = np.stack([O.clip_preprocess(im, geom.image_resolution) for im in images_u8])
-    feats = O.encode_image(sd_np, x)
-    return O.score(feats, sd_np["visual.proj"], text_w, 100.0, 1)
+class CpuReference:
+    """The reference's CPU fp32 path for this workload: oracle/clip_oracle_torch.py, i.e. the torch operators the
+    reference itself calls on CPU (PIL / torchvision preprocessing per image, conv2d, LayerNorm,
+    multi_head_attention_forward, Linear, QuickGELU, normalize, argmax), on all host threads."""
+
+    def __init__(self, geom, sd_np, text_w):
+        import torch
+        from oracle import clip_oracle_torch as OT
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arms are meant to use every host core
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.cores = torch.get_num_threads()
+        self.OT, self.R = OT, geom.image_resolution
+        self.sd = OT.to_torch_state(sd_np)
+        self.text_w = torch.as_tensor(np.asarray(text_w), dtype=torch.float32)
+
+    def __call__(self, images_u8):
+        return self.OT.reference_pass(self.sd, self.text_w, images_u8, self.R)
 
 
-def use_all_host_threads() -> int:
-    """torchrun exports OMP_NUM_THREADS=1; the CPU arms are meant to use every host core, so lift the BLAS pool
-    limit at run time (threadpoolctl) and report what is actually in effect."""
-    n = os.cpu_count() or 1
-    try:
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=n)
-    except Exception:
-        pass
-    return blas_threads()
-
-
-def blas_threads() -> int:
-    try:
-        from threadpoolctl import threadpool_info
-        n = [d.get("num_threads", 0) for d in threadpool_info() if d.get("user_api") == "blas"]
-        if n:
-            return max(n)
-    except Exception:
-        pass
-    return os.cpu_count() or 1
+CPU_KIND_NOTE = ("torch-operator restatement of the reference CPU path (oracle/clip_oracle_torch.py; the reference "
+                 "itself is Python under /root/reference and cannot travel to the GPU box)")
 
 
 def run_reference(args):
@@ -140,16 +132,17 @@ def run_reference(args):
         return 0
     from aihab_clip_b200.weights import GEOMETRIES, make_state_dict_np, synthetic_images_u8
     geom = GEOMETRIES[args.arch]
-    cores = use_all_host_threads()
     sd = make_state_dict_np(geom, 0, with_text=False)
     text_w = cpu_text_head(sd, args.classes, geom.embed_dim)
+    ref = CpuReference(geom, sd, text_w)
+    cores = ref.cores
     n = args.ref_batch
     imgs = synthetic_images_u8(n, geom.image_resolution)
     for _ in range(args.warmup):
-        cpu_reference_pass(geom, sd, text_w, imgs[:max(1, n // 4)])
+        ref(imgs[:max(1, n // 4)])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_pass(geom, sd, text_w, imgs)
+        ref(imgs)
     dt = time.perf_counter() - t0
     val = args.steps * n / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
@@ -157,10 +150,10 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.arch, geom.image_resolution, args.classes), "arch": args.arch,
                        "classes": args.classes, "weights": "random-init (aihab_clip_b200.weights seed 0)",
-                       "images_per_step": n, "operands": "fp32 (numpy oracle port of the reference CPU path)"},
+                       "images_per_step": n, "operands": "fp32, " + CPU_KIND_NOTE},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{n} images per step x {args.steps} steps, numpy fp32 oracle port of the "
-                                       "reference CPU path (reference itself is Python and cannot travel)"},
+                             "sample": f"{n} images per step x {args.steps} steps (the reference's shipped extraction "
+                                       f"batch is 16, methods/utils.py:142-173); {CPU_KIND_NOTE}"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -346,21 +339,19 @@ def run_b200(args):
         # CPU baseline on a bounded sample (rank 0, N = 1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = use_all_host_threads()
             sd_np = make_state_dict_np(geom, 0, with_text=False)
-            tw = text_w.cpu().numpy()
+            ref = CpuReference(geom, sd_np, text_w.cpu().numpy())
             n_cpu = args.cpu_images
             imgs = synthetic_images_u8(n_cpu, R)
-            cpu_reference_pass(geom, sd_np, tw, imgs[:1])
+            ref(imgs[:2])
             t0 = time.perf_counter()
             reps = 0
-            while reps < 1 or (time.perf_counter() - t0 < 10.0 and reps < 8):
-                cpu_reference_pass(geom, sd_np, tw, imgs)
+            while reps < 1 or (time.perf_counter() - t0 < 10.0 and reps < 16):
+                ref(imgs)
                 reps += 1
             dt = time.perf_counter() - t0
-            cpu = {"value": reps * n_cpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{reps} x {n_cpu} images of the same workload through the numpy fp32 oracle port "
-                             f"({dt:.1f} s)"}
+            cpu = {"value": reps * n_cpu / dt, "unit": UNIT, "cores": ref.cores, "kind": "port",
+                   "sample": f"{reps} x {n_cpu} images of the same workload ({dt:.1f} s); {CPU_KIND_NOTE}"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -405,8 +396,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--classes", type=int, default=20)
-    ap.add_argument("--ref-batch", type=int, default=8, help="--impl reference: images per step (bounded sample)")
-    ap.add_argument("--cpu-images", type=int, default=8, help="cpu_baseline sample size per repetition")
+    ap.add_argument("--ref-batch", type=int, default=16, help="--impl reference: images per step (bounded sample)")
+    ap.add_argument("--cpu-images", type=int, default=16, help="cpu_baseline sample size per repetition")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true",
                     help="do not record per-launch CUDA events in the timed region (roofline becomes 0)")

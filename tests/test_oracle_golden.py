@@ -137,3 +137,24 @@ def test_prototype_scores_match_reference_golden():
     _, _, o1, m1 = O.prototype_scores(g["emb"][one], g["labels"][one], g["prototypes"][g["owner"] == g["labels"][0]],
                                       g["owner"][g["owner"] == g["labels"][0]])
     assert np.isnan(o1).all() and np.isnan(m1).all()
+
+
+@pytest.mark.parametrize("tag", ["tiny16", "tiny14", "b32"])
+def test_torch_restatement_matches_reference(gold, tag):
+    """oracle/clip_oracle_torch.py (the restatement timed as the CPU reference arm) against the same reference
+    goldens: preprocessing bit-exact, features / logits within the numpy oracle's tolerances, identical top-3."""
+    import torch
+    from oracle import clip_oracle_torch as OT
+    geom, sd, u8 = case_inputs(tag)
+    x = OT.preprocess_pil(u8, geom.image_resolution)
+    assert sha(x.numpy()) == gold[f"{tag}_pre_sha"].tobytes(), "preprocessing must be bit-exact"
+    sdt = OT.to_torch_state(sd)
+    feats = OT.encode_image(sdt, x)
+    np.testing.assert_allclose(feats.numpy(), gold[f"{tag}_feats"], atol=2e-4, rtol=0)
+    emb, logits, top3 = OT.score(feats, sdt["visual.proj"], torch.from_numpy(gold[f"{tag}_text_w"]), 100.0, 3)
+    np.testing.assert_allclose(emb.numpy(), gold[f"{tag}_emb"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(logits.numpy(), gold[f"{tag}_logits"], atol=5e-4, rtol=0)
+    ref = gold[f"{tag}_logits"]
+    gaps = np.abs(np.diff(np.sort(ref, axis=1)[:, ::-1][:, :4], axis=1)).min(axis=1)
+    untied = gaps > 2e-3
+    assert (top3.numpy()[untied] == gold[f"{tag}_top3"][untied]).all()
