@@ -346,7 +346,7 @@ def run_b200(args):
             ref(imgs[:2])
             t0 = time.perf_counter()
             reps = 0
-            while reps < 1 or (time.perf_counter() - t0 < 10.0 and reps < 16):
+            while reps < 1 or (time.perf_counter() - t0 < 10.0 and reps < 64):
                 ref(imgs)
                 reps += 1
             dt = time.perf_counter() - t0
