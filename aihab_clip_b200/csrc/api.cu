@@ -88,7 +88,8 @@ int fail(const std::string& msg) {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-// attention kernel choice: 3 = persistent flash tcgen05 (L > 224), 2 = persistent tcgen05 (64 < L <= 224),
+// attention kernel choice: 3 = persistent flash tcgen05 (L > 224), 2 = persistent tcgen05 (16 <= L <= 224; images
+// packed block-diagonally for L <= 64),
 // 1 = tcgen05 (L <= 256), 0 = mma.sync (any L <= 908).
 // AIHAB_ATTN=legacy|tc|tcp caps the choice (A/B measurements); default picks the fastest supported kernel.
 int attention_kind(int L) {
@@ -103,7 +104,9 @@ int attention_kind(int L) {
   if (cap >= 1 && aihab::attention_tc_supported(L)) return 1;
   return 0;
 }
-int attention_key_box(int kind, int L) { return kind == 3 ? 32 : aihab::attention_tc_key_rows(L); }
+int attention_key_box(int kind, int L) {
+  return kind == 3 ? 32 : (kind == 2 ? aihab::attention_tcp_key_rows(L) : aihab::attention_tc_key_rows(L));
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -1197,7 +1200,8 @@ int aihab_layernorm(const float* x, int rows, int D, const float* gamma, const f
 int aihab_attention_causal(const void* qkv, void* out, int n, int L, int H, int dtype, void* stream) {
   if (qkv == nullptr || out == nullptr || n < 0) return fail("aihab_attention_causal: bad argument");
   if (dtype != AIHAB_F16 && dtype != AIHAB_BF16) return fail("aihab_attention_causal: dtype must be AIHAB_F16 or AIHAB_BF16");
-  if (!aihab::attention_tcp_supported(L)) return fail("aihab_attention_causal: needs 64 < L <= 224");
+  if (!aihab::attention_tcp_supported(L) || aihab::attention_tcp_pack(L) != 1)
+    return fail("aihab_attention_causal: needs 64 < L <= 224");
   DeviceGuard guard(device_of(qkv));
   if (n == 0) return 0;
   CUtensorMap mq, mkv;
@@ -1205,7 +1209,7 @@ int aihab_attention_causal(const void* qkv, void* out, int n, int L, int H, int 
   const uint64_t rows = static_cast<uint64_t>(n) * L, pitch = static_cast<uint64_t>(3 * H * 64) * 2;
   CK(aihab::gemm_init());
   CK(aihab::make_tmap_2d_16bit(&mq, qkv, rows, 3 * H * 64, pitch, 128, bf16));
-  CK(aihab::make_tmap_2d_16bit(&mkv, qkv, rows, 3 * H * 64, pitch, aihab::attention_tc_key_rows(L), bf16));
+  CK(aihab::make_tmap_2d_16bit(&mkv, qkv, rows, 3 * H * 64, pitch, aihab::attention_tcp_key_rows(L), bf16));
   CKL(aihab::launch_attention_tcp(mq, mkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream),
                                   0, 1));
   return 0;

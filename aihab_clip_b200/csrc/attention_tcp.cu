@@ -10,7 +10,11 @@
 //                                   16-bit pairs over the S columns (tcgen05.st) - the PV MMA takes A from TMEM, so P
 //                                   never touches shared memory; the O(i-1) epilogue (TMEM -> 1/sum -> global) runs
 //                                   before the hand-off, hiding the PV MMA of the previous item
-// TMEM: S0/P0 [0,224) S1/P1 [224,448) O [448,512).  smem: 2 x (Q 16 KB + K 28 KB + V 28 KB) = 144 KB.
+// Short sequences (16 <= L <= 64, ViT-B/32: L = 50) are PACKED: g = 128 / L consecutive images of the same head form one
+// "sequence" of g * L rows (they are contiguous rows of the qkv buffer), one S = Q K^T covers all of them and a
+// block-diagonal mask (query row r sees keys [r / L * L, r / L * L + L)) keeps the images apart; P is zero outside the
+// row's own block, so O = P V over the stacked V rows is already the per-image result.
+// TMEM: S0/P0 [0,224) S1/P1 [224,448) O [448,512).  smem: NS x (Q 16 KB + K Lk x 128 B + V Lk x 128 B), NS = 2..4.
 // Reference: clip/model.py:179-181 (nn.MultiheadAttention core: softmax(q k^T / sqrt(64)) v, no mask).
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
@@ -22,26 +26,33 @@ namespace {
 
 constexpr int P_THREADS = 320;
 constexpr int KV_MAX = 224;
+// shared memory: NS input stages of (Q 16 KB | K Lk x 128 B | V Lk x 128 B), sized by the launch for its Lk - three
+// stages at Lk = 208, four for the packed short sequences (their per-item work is small, so the loads have to be
+// requested further ahead) - then the barriers and the row max / sum exchange
+constexpr int NS_MAX = 4;
 constexpr int ST_Q = 0;
 constexpr int ST_K = 16384;
-constexpr int ST_V = ST_K + KV_MAX * 128;
-constexpr int ST_BYTES = ST_V + KV_MAX * 128;  // 73728
-constexpr int OFF_BAR = 2 * ST_BYTES;
-constexpr int OFF_RED = OFF_BAR + 128;         // s_max[2][256], s_sum[2][256]
-constexpr int P_SMEM = OFF_RED + 4096 + 1024;
+__host__ __device__ constexpr int st_v(int Lk) { return ST_K + Lk * 128; }
+__host__ __device__ constexpr int st_bytes(int Lk) { return ST_K + 2 * Lk * 128; }  // Lk = 224: 73728
+constexpr int RED_BYTES = 4096;  // s_max[2][256], s_sum[2][256]
+constexpr int BAR_BYTES = 256;
+__host__ __device__ constexpr int smem_bytes(int Lk, int ns) { return ns * st_bytes(Lk) + BAR_BYTES + RED_BYTES + 1024; }
+constexpr int SMEM_CAP = 227 * 1024;
 constexpr int TM_S = 224;                      // TMEM columns per S buffer
 constexpr int TM_O = 448;
-static_assert(ST_K % 1024 == 0 && ST_V % 1024 == 0 && ST_BYTES % 1024 == 0, "SWIZZLE_128B tiles need 1024 B alignment");
-static_assert(P_SMEM <= 227 * 1024, "smem budget");
+static_assert(ST_K % 1024 == 0 && st_v(16) % 1024 == 0 && st_bytes(16) % 1024 == 0, "SWIZZLE_128B tiles need 1024 B alignment");
+static_assert(smem_bytes(KV_MAX, 2) <= SMEM_CAP, "smem budget");
 
 // Softmax of one query row half for one item, fully unrolled over NC 16-column chunks: the S values are read from
 // TMEM ONCE (NC x tcgen05.ld.x16 in flight together) and stay in registers across the row-max exchange.
 // Columns >= L are masked; only the last two chunks of a thread's range can contain such columns.
-// CAUSAL (text tower, clip/model.py:323-329): L is the row's own limit min(L, query index + 1), and any chunk can hold
-// masked columns.
-template <bool BF16, int NC, bool CAUSAL>
-__device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L, float sl2, float* s_max_b,
+// MASK 1 (causal, text tower, clip/model.py:323-329): L is the row's own limit min(L, query index + 1), and any chunk
+// can hold masked columns.  MASK 2 (block-diagonal, packed short sequences): the row sees columns [lo, L).
+enum : int { MASK_NONE = 0, MASK_CAUSAL = 1, MASK_BLOCK = 2 };
+template <bool BF16, int NC, int MASK>
+__device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int lo, int L, float sl2, float* s_max_b,
                                              float* s_sum_b, int half, int row, bool has_rows) {
+  constexpr bool CAUSAL = MASK != MASK_NONE;  // per-row limits: every chunk takes the masked path
   uint32_t r[NC][16];
   if (has_rows) {
 #pragma unroll
@@ -58,8 +69,10 @@ __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L,
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if ((c_begin + i) * 16 + j < L) m0 = fmaxf(m0, __uint_as_float(r[i][j]));
+        for (int j = 0; j < 16; ++j) {
+          const int col = (c_begin + i) * 16 + j;
+          if (col < L && (MASK != MASK_BLOCK || col >= lo)) m0 = fmaxf(m0, __uint_as_float(r[i][j]));
+        }
       }
     }
     s_max_b[half * 128 + row] = fmaxf(m0, m1);
@@ -81,8 +94,8 @@ __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L,
         float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[i][2 * j]), sl2, -ms));
         float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[i][2 * j + 1]), sl2, -ms));
         if (CAUSAL || i >= NC - 2) {
-          if (c * 16 + 2 * j >= L) p0 = 0.f;
-          if (c * 16 + 2 * j + 1 >= L) p1 = 0.f;
+          if (c * 16 + 2 * j >= L || (MASK == MASK_BLOCK && c * 16 + 2 * j < lo)) p0 = 0.f;
+          if (c * 16 + 2 * j + 1 >= L || (MASK == MASK_BLOCK && c * 16 + 2 * j + 1 < lo)) p1 = 0.f;
         }
         l0 += p0;
         l1 += p1;
@@ -95,22 +108,26 @@ __device__ __forceinline__ void softmax_item(uint32_t t_row, int c_begin, int L,
   }
 }
 
-template <bool BF16, int NC, bool CAUSAL>
+// L = rows per sequence (one image, or g packed images of Lblk rows each with MASK_BLOCK); rows_total = valid rows
+// of the qkv buffer (the last packed sequence may hold fewer than g images).
+template <bool BF16, int NC, int MASK>
 __global__ void __launch_bounds__(P_THREADS, 1)
 attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                     uint16_t* __restrict__ out, int L, int H, int Lk, int nq, int total, int reverse) {
+                     uint16_t* __restrict__ out, int L, int H, int Lk, int nq, int total, int reverse, int Lblk,
+                     int rows_total, int NS) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024 B aligned, still a __shared__ pointer
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* bar_qk = bars + 0;      // [2] Q + K of a stage landed
-  uint64_t* bar_v = bars + 2;       // [2] V of a stage landed
-  uint64_t* bar_stfree = bars + 4;  // [2] stage inputs consumed (commit after PV)
-  uint64_t* bar_sfull = bars + 6;   // [2] S buffer written
-  uint64_t* bar_pvdone = bars + 8;  // [2] PV MMA of the item using S/P buffer b retired: the buffer is free
-  uint64_t* bar_p = bars + 10;      // P written to TMEM (and O of the previous item read)
-  uint64_t* bar_o = bars + 11;      // O written
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  float* s_max = reinterpret_cast<float*>(smem + OFF_RED);  // [2][256]
+  const int ST_V = st_v(Lk), ST_BYTES = st_bytes(Lk);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * ST_BYTES);
+  uint64_t* bar_qk = bars + 0;                   // [NS] Q + K of a stage landed
+  uint64_t* bar_v = bars + NS_MAX;               // [NS] V of a stage landed
+  uint64_t* bar_stfree = bars + 2 * NS_MAX;      // [NS] stage inputs consumed (commit after PV)
+  uint64_t* bar_sfull = bars + 3 * NS_MAX;       // [2] S buffer written
+  uint64_t* bar_pvdone = bars + 3 * NS_MAX + 2;  // [2] PV MMA of the item using S/P buffer b retired: the buffer is free
+  uint64_t* bar_p = bars + 3 * NS_MAX + 4;       // P written to TMEM (and O of the previous item read)
+  uint64_t* bar_o = bars + 3 * NS_MAX + 5;       // O written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NS_MAX + 6);
+  float* s_max = reinterpret_cast<float*>(smem + NS * ST_BYTES + BAR_BYTES);  // [2][256]
   float* s_sum = s_max + 512;                               // [2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,10 +155,12 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (lane == 0) {
       ptx::prefetch_tmap(&tmap_q);
       ptx::prefetch_tmap(&tmap_kv);
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NS; ++i) {
         ptx::mbar_init(&bar_qk[i], 1);
         ptx::mbar_init(&bar_v[i], 1);
         ptx::mbar_init(&bar_stfree[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&bar_sfull[i], 1);
         ptx::mbar_init(&bar_pvdone[i], 1);
       }
@@ -165,9 +184,9 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       for (int it = 0; it < n_items; ++it) {
         int img, h, qt;
         decode(it, img, h, qt);
-        const int s = it & 1, k = it >> 1;
+        const int s = it % NS, k = it / NS;  // input stage and its use count
         uint8_t* st = smem + s * ST_BYTES;
-        if (it >= 2) ptx::mbar_wait(&bar_stfree[s], (k - 1) & 1);
+        if (it >= NS) ptx::mbar_wait(&bar_stfree[s], (k - 1) & 1);
         const int row0 = img * L;
         ptx::mbar_expect_tx(&bar_qk[s], 128 * 128 + Lk * 128);
         ptx::tma_load_2d(st + ST_Q, &tmap_q, &bar_qk[s], h * 64, row0 + qt * 128);
@@ -183,32 +202,32 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint32_t idesc_o = ptx::make_idesc_f16(BF16 ? 1 : 0, 128, 64, /*b_mn_major=*/1);
       const int ksteps = Lk >> 4;
       auto issue_s = [&](int it) {
-        const int s = it & 1, k = it >> 1;
-        ptx::mbar_wait(&bar_qk[s], k & 1);
-        if (it >= 2) ptx::mbar_wait(&bar_pvdone[s], (k - 1) & 1);  // P(it-2) lives in this buffer until PV(it-2) retires
+        const int s = it % NS, b = it & 1;  // input stage; S/P buffer in TMEM
+        ptx::mbar_wait(&bar_qk[s], (it / NS) & 1);
+        if (it >= 2) ptx::mbar_wait(&bar_pvdone[b], ((it >> 1) - 1) & 1);  // P(it-2) lives in this buffer until PV(it-2) retires
         ptx::tc_fence_after();
         const uint32_t st = ptx::smem_u32(smem + s * ST_BYTES);
         const uint64_t qd = ptx::make_kmajor_sw128_desc(st + ST_Q);
         const uint64_t kd = ptx::make_kmajor_sw128_desc(st + ST_K);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + s * TM_S, qd + 2 * kk, kd + 2 * kk, idesc_s, kk != 0);
-        ptx::umma_commit(&bar_sfull[s]);
+        for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + b * TM_S, qd + 2 * kk, kd + 2 * kk, idesc_s, kk != 0);
+        ptx::umma_commit(&bar_sfull[b]);
       };
       if (n_items > 0) issue_s(0);
       for (int it = 0; it < n_items; ++it) {
         if (it + 1 < n_items) issue_s(it + 1);
-        const int s = it & 1, k = it >> 1;
+        const int s = it % NS, b = it & 1;
         ptx::mbar_wait(bar_p, it & 1);
-        ptx::mbar_wait(&bar_v[s], k & 1);
+        ptx::mbar_wait(&bar_v[s], (it / NS) & 1);
         ptx::tc_fence_after();
         const uint32_t v_base = ptx::smem_u32(smem + s * ST_BYTES + ST_V);
         for (int j = 0; j < ksteps; ++j) {
           const uint64_t vd = ptx::make_mnmajor_sw128_desc(v_base + j * 2048);
-          ptx::umma_f16_ts(tmem + TM_O, tmem + s * TM_S + j * 8, vd, idesc_o, j != 0);  // A = P from TMEM
+          ptx::umma_f16_ts(tmem + TM_O, tmem + b * TM_S + j * 8, vd, idesc_o, j != 0);  // A = P from TMEM
         }
         ptx::umma_commit(bar_o);
         ptx::umma_commit(&bar_stfree[s]);
-        ptx::umma_commit(&bar_pvdone[s]);
+        ptx::umma_commit(&bar_pvdone[b]);
       }
     }
   } else {
@@ -224,11 +243,12 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // O(prev) -> global: this thread owns 32 of the 64 output columns of its row
     auto epilogue = [&](int img, int h, int qt, int b) {
       if (qt * 128 + quad * 32 >= L) return;
+      const int valid = MASK == MASK_BLOCK ? min(L, rows_total - img * L) : L;  // rows of this sequence that exist
       uint32_t o[32];
       ptx::tmem_ld_32x32(tmem + lane_off + TM_O + half * 32, o);
       ptx::tmem_ld_wait();
       const int grow = qt * 128 + row;
-      if (grow < L) {
+      if (grow < valid) {
         const float inv_l = 1.0f / (s_sum[b * 256 + row] + s_sum[b * 256 + 128 + row]);
         uint16_t* dst = out + (static_cast<size_t>(img) * L + grow) * D + h * 64 + half * 32;
 #pragma unroll
@@ -253,8 +273,14 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
       ptx::mbar_wait(&bar_sfull[b], k & 1);
       ptx::tc_fence_after();
-      const int lim = CAUSAL ? min(L, qt * 128 + row + 1) : L;  // valid key columns of this thread's row
-      softmax_item<BF16, NC, CAUSAL>(t_row, c_begin, lim, sl2, s_max + b * 256, s_sum + b * 256, half, row, has_rows);
+      // valid key columns [lo, lim) of this thread's row
+      int lo = 0, lim = L;
+      if (MASK == MASK_CAUSAL) lim = min(L, qt * 128 + row + 1);
+      if (MASK == MASK_BLOCK) {
+        lo = min(row / Lblk, L / Lblk - 1) * Lblk;  // tile rows past the sequence reuse the last block (never stored)
+        lim = lo + Lblk;
+      }
+      softmax_item<BF16, NC, MASK>(t_row, c_begin, lo, lim, sl2, s_max + b * 256, s_sum + b * 256, half, row, has_rows);
       if (it > 0) {  // O(it-1): its PV was issued a whole softmax ago
         ptx::mbar_wait(bar_o, (it - 1) & 1);
         ptx::tc_fence_after();
@@ -281,55 +307,70 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   }
 }
 
-template <bool BF16, int NC, bool CAUSAL>
+template <bool BF16, int NC, int MASK>
 cudaError_t launch_nc(const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* out, int L, int H, int Lk, int nq,
-                      int total, int grid, int reverse, cudaStream_t stream) {
+                      int total, int grid, int reverse, int Lblk, int rows_total, cudaStream_t stream) {
   static bool attr_set[64] = {};  // per device
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcp_kernel<BF16, NC, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_tcp_kernel<BF16, NC, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  return launch_kernel(attention_tcp_kernel<BF16, NC, CAUSAL>, grid, P_THREADS, P_SMEM, stream, 1, true, tq, tkv, out, L, H, Lk, nq,
-                       total, reverse);
+  // as many input stages as fit (2..NS_MAX); AIHAB_ATTN_STAGES caps them for A/B runs
+  int ns = NS_MAX;
+  if (const char* e = getenv("AIHAB_ATTN_STAGES")) ns = atoi(e) < 2 ? 2 : (atoi(e) > NS_MAX ? NS_MAX : atoi(e));
+  while (ns > 2 && smem_bytes(Lk, ns) > SMEM_CAP) --ns;
+  return launch_kernel(attention_tcp_kernel<BF16, NC, MASK>, grid, P_THREADS, smem_bytes(Lk, ns), stream, 1, true, tq, tkv, out, L, H,
+                       Lk, nq, total, reverse, Lblk, rows_total, ns);
 }
 
-template <bool BF16, bool CAUSAL>
+template <bool BF16, int MASK>
 cudaError_t launch_dt(int nc, const CUtensorMap& tq, const CUtensorMap& tkv, uint16_t* out, int L, int H, int Lk,
-                      int nq, int total, int grid, int reverse, cudaStream_t stream) {
+                      int nq, int total, int grid, int reverse, int Lblk, int rows_total, cudaStream_t stream) {
   switch (nc) {
-    case 3: return launch_nc<BF16, 3, CAUSAL>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
-    case 4: return launch_nc<BF16, 4, CAUSAL>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
-    case 5: return launch_nc<BF16, 5, CAUSAL>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
-    case 6: return launch_nc<BF16, 6, CAUSAL>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
-    case 7: return launch_nc<BF16, 7, CAUSAL>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, stream);
+    case 3: return launch_nc<BF16, 3, MASK>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, Lblk, rows_total, stream);
+    case 4: return launch_nc<BF16, 4, MASK>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, Lblk, rows_total, stream);
+    case 5: return launch_nc<BF16, 5, MASK>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, Lblk, rows_total, stream);
+    case 6: return launch_nc<BF16, 6, MASK>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, Lblk, rows_total, stream);
+    case 7: return launch_nc<BF16, 7, MASK>(tq, tkv, out, L, H, Lk, nq, total, grid, reverse, Lblk, rows_total, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
 }  // namespace
 
-bool attention_tcp_supported(int L) { return L > 64 && (L + 15) / 16 * 16 <= KV_MAX; }
+// images packed into one sequence: 1 for L > 64, else as many whole images as fit 128 query rows
+int attention_tcp_pack(int L) { return L > 64 ? 1 : 128 / L; }
+bool attention_tcp_supported(int L) { return L >= 16 && (L * attention_tcp_pack(L) + 15) / 16 * 16 <= KV_MAX; }
+int attention_tcp_key_rows(int L) { return (L * attention_tcp_pack(L) + 15) / 16 * 16; }
 
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
                                  int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse, int causal) {
   if (n_img <= 0) return cudaSuccess;
   if (!attention_tcp_supported(L)) return cudaErrorInvalidValue;
-  const int Lk = (L + 15) / 16 * 16;
-  const int nq = (L + 127) / 128;
-  const int total = n_img * H * nq;
+  const int g = attention_tcp_pack(L);
+  if (g > 1 && causal) return cudaErrorInvalidValue;  // the text tower has L = 77
+  const int Ls = g * L;                       // rows per sequence
+  const int n_seq = (n_img + g - 1) / g;
+  const int Lk = (Ls + 15) / 16 * 16;
+  const int nq = (Ls + 127) / 128;
+  const int total = n_seq * H * nq;
   int grid = total < num_sms ? total : num_sms;
   if (nq == 2) grid &= ~1;  // even: a CTA's items alternate between the full and the partial query tile
   const int nc = ((Lk >> 4) + 1) >> 1;
+  const int rows_total = n_img * L;
   uint16_t* o = static_cast<uint16_t*>(out);
+  if (g > 1)
+    return is_bf16 ? launch_dt<true, MASK_BLOCK>(nc, tmap_q, tmap_kv, o, Ls, H, Lk, nq, total, grid, reverse, L, rows_total, stream)
+                   : launch_dt<false, MASK_BLOCK>(nc, tmap_q, tmap_kv, o, Ls, H, Lk, nq, total, grid, reverse, L, rows_total, stream);
   if (causal)
-    return is_bf16 ? launch_dt<true, true>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream)
-                   : launch_dt<false, true>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream);
-  return is_bf16 ? launch_dt<true, false>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream)
-                 : launch_dt<false, false>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, stream);
+    return is_bf16 ? launch_dt<true, MASK_CAUSAL>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, L, rows_total, stream)
+                   : launch_dt<false, MASK_CAUSAL>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, L, rows_total, stream);
+  return is_bf16 ? launch_dt<true, MASK_NONE>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, L, rows_total, stream)
+                 : launch_dt<false, MASK_NONE>(nc, tmap_q, tmap_kv, o, L, H, Lk, nq, total, grid, reverse, L, rows_total, stream);
 }
 
 }  // namespace aihab

@@ -41,9 +41,13 @@ int attention_tc_key_rows(int L);
 cudaError_t launch_attention_tc(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
                                 int H, int is_bf16, cudaStream_t stream);
 
-// Persistent, software-pipelined variant (64 < L <= 224): one CTA per SM, double-buffered Q/K/V stages and S buffers,
-// epilogue of item i-1 overlapped with the PV MMA.  Same tensor maps as launch_attention_tc.
+// Persistent, software-pipelined variant (16 <= L <= 224; for L <= 64 several images share a tile behind a
+// block-diagonal mask): one CTA per SM, double-buffered Q/K/V stages and S buffers,
+// epilogue of item i-1 overlapped with the PV MMA.  Tensor maps as for launch_attention_tc, K / V box of
+// attention_tcp_key_rows(L) rows.
 bool attention_tcp_supported(int L);
+int attention_tcp_pack(int L);      // images per packed sequence (1 for L > 64)
+int attention_tcp_key_rows(int L);  // rows of the K / V TMA box
 // causal != 0: key j is visible to query i only if j <= i (the text tower's attn_mask, clip/model.py:323-329).
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
                                  int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse = 0, int causal = 0);
