@@ -88,8 +88,8 @@ int fail(const std::string& msg) {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-// attention kernel choice: 3 = persistent flash tcgen05 (L > 224), 2 = persistent tcgen05 (16 <= L <= 224; images
-// packed block-diagonally for L <= 64),
+// attention kernel choice: 3 = persistent flash tcgen05 (L > 224), 2 = persistent tcgen05 (64 < L <= 224; with
+// AIHAB_ATTN_PACK=1 also 16 <= L <= 64, images packed block-diagonally),
 // 1 = tcgen05 (L <= 256), 0 = mma.sync (any L <= 908).
 // AIHAB_ATTN=legacy|tc|tcp caps the choice (A/B measurements); default picks the fastest supported kernel.
 int attention_kind(int L) {

@@ -342,9 +342,22 @@ cudaError_t launch_dt(int nc, const CUtensorMap& tq, const CUtensorMap& tkv, uin
 
 }  // namespace
 
-// images packed into one sequence: 1 for L > 64, else as many whole images as fit 128 query rows
-int attention_tcp_pack(int L) { return L > 64 ? 1 : 128 / L; }
-bool attention_tcp_supported(int L) { return L >= 16 && (L * attention_tcp_pack(L) + 15) / 16 * 16 <= KV_MAX; }
+// images packed into one sequence: 1 for L > 64, else as many whole images as fit 128 query rows.
+// OPT-IN (AIHAB_ATTN_PACK=1): where an image's keys fall inside the 16-key MMA steps depends on its position in the
+// pack, so the fp32 accumulation order of O - and with it the last bits of the result - depends on which images share
+// a tile.  The extraction path promises per-image results that are bit-identical for every batch composition and
+// shard count, so the default keeps one image per sequence and L <= 64 on the mma.sync kernel.
+int attention_tcp_pack(int L) {
+  static const bool enabled = [] {  // read once: tensor maps built at create and launches must agree
+    const char* e = getenv("AIHAB_ATTN_PACK");
+    return e != nullptr && e[0] == '1';
+  }();
+  return (L > 64 || !enabled) ? 1 : 128 / L;
+}
+bool attention_tcp_supported(int L) {
+  const int g = attention_tcp_pack(L);
+  return L >= 16 && (L > 64 || g > 1) && (L * g + 15) / 16 * 16 <= KV_MAX;
+}
 int attention_tcp_key_rows(int L) { return (L * attention_tcp_pack(L) + 15) / 16 * 16; }
 
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,

@@ -41,8 +41,8 @@ int attention_tc_key_rows(int L);
 cudaError_t launch_attention_tc(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
                                 int H, int is_bf16, cudaStream_t stream);
 
-// Persistent, software-pipelined variant (16 <= L <= 224; for L <= 64 several images share a tile behind a
-// block-diagonal mask): one CTA per SM, double-buffered Q/K/V stages and S buffers,
+// Persistent, software-pipelined variant (64 < L <= 224; opt-in for 16 <= L <= 64, where several images share a tile
+// behind a block-diagonal mask): one CTA per SM, double-buffered Q/K/V stages and S buffers,
 // epilogue of item i-1 overlapped with the PV MMA.  Tensor maps as for launch_attention_tc, K / V box of
 // attention_tcp_key_rows(L) rows.
 bool attention_tcp_supported(int L);
