@@ -11,9 +11,11 @@ hdr = rows[start]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 agg = collections.OrderedDict()
 for r in rows[start + 1:]:
-    if len(r) <= vi or (not keep_all and "aihab::" not in r[ki]):
+    # this library's kernels live in aihab::<unnamed>; depending on the ncu name base the CSV shows "aihab::..." or
+    # the tail "unnamed>::..."
+    if len(r) <= vi or (not keep_all and "aihab::" not in r[ki] and "unnamed>::" not in r[ki]):
         continue
-    name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("aihab::<unnamed>::", "")[:64]
+    name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("aihab::<unnamed>::", "").replace("unnamed>::", "")[:64]
     v = float(r[vi].replace(",", ""))
     v = v / 1000 if r[ui] == "ns" else (v * 1000 if r[ui] == "ms" else v)
     a = agg.setdefault(name, [0, 0.0])
