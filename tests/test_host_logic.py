@@ -187,3 +187,33 @@ def test_preferred_batch_fills_whole_waves():
     b = lib.aihab_preferred_batch(50, 768, 1024, 0)
     pair_tiles = -(-b * 50 // 256)
     assert pair_tiles % 74 == 0  # ViT-B/32: 757 images = 148 tile pairs = 2 per SM pair
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exits 0 without a GPU, prints exactly one
+    JSON line with the base contract's keys plus impl / cpu_baseline / e2e, and times the torch-operator restatement."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    repo = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(repo / "bench.py"), "--impl", "reference", "--arch", "ViT-tiny/16",
+                          "--steps", "2", "--warmup", "1", "--ref-batch", "4"], capture_output=True, text=True,
+                         timeout=300, cwd=repo)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["steps"] == 2
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert "clip_oracle_torch" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # rank != 0 of a torchrun launch exits 0 without work and without output
+    import os
+    env = dict(os.environ, RANK="1")
+    quiet = subprocess.run([sys.executable, str(repo / "bench.py"), "--impl", "reference", "--arch", "ViT-tiny/16"],
+                           capture_output=True, text=True, timeout=300, cwd=repo, env=env)
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
