@@ -27,6 +27,12 @@ def gold():
 
 
 @pytest.fixture(scope="session")
+def gold_vitl():
+    """Reference outputs at the ViT-L/14 widths / sequence lengths (tests/golden/make_golden_vitl.py)."""
+    return np.load(GOLDEN / "reference_outputs_vitl.npz")
+
+
+@pytest.fixture(scope="session")
 def meta():
     return json.loads((GOLDEN / "reference_meta.json").read_text())
 

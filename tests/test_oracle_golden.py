@@ -158,3 +158,25 @@ def test_torch_restatement_matches_reference(gold, tag):
     gaps = np.abs(np.diff(np.sort(ref, axis=1)[:, ::-1][:, :4], axis=1)).min(axis=1)
     untied = gaps > 2e-3
     assert (top3.numpy()[untied] == gold[f"{tag}_top3"][untied]).all()
+
+
+@pytest.mark.parametrize("tag,geom_name,n", [("lmini", "ViT-L-mini/14", 5), ("lmini336", "ViT-L-mini/14@336px", 3)])
+def test_vit_l_geometries_are_pinned_to_the_reference(gold_vitl, tag, geom_name, n):
+    """BASELINE.json configs 3 and 4 (ViT-L/14: width 1024, 16 heads, 257 / 577 tokens, 588-wide patches): both
+    restatements against outputs of the unmodified reference on the inputs of the GPU parity test
+    (tests/test_gpu_model.py::test_vit_l_geometries_match_oracle)."""
+    import torch
+    from oracle import clip_oracle_torch as OT
+    geom = GEOMETRIES[geom_name]
+    sd = make_state_dict_np(geom, 3, with_text=False)
+    u8 = synthetic_images_u8(n, 300, smooth=True)
+    x = np.stack([O.clip_preprocess(im, geom.image_resolution) for im in u8])
+    assert sha(x) == gold_vitl[f"{tag}_pre_sha"].tobytes(), "preprocessing must be bit-exact"
+    feats = O.encode_image(sd, x)
+    np.testing.assert_allclose(feats, gold_vitl[f"{tag}_feats"], atol=3e-4, rtol=0)
+    emb, _, _ = O.score(feats, sd["visual.proj"], np.eye(geom.embed_dim, 4, dtype=np.float32), 100.0, 1)
+    np.testing.assert_allclose(emb, gold_vitl[f"{tag}_emb"], atol=5e-6, rtol=0)
+    sdt = OT.to_torch_state(sd)
+    xt = OT.preprocess_pil(u8, geom.image_resolution)
+    assert sha(xt.numpy()) == gold_vitl[f"{tag}_pre_sha"].tobytes()
+    np.testing.assert_allclose(OT.encode_image(sdt, xt).numpy(), gold_vitl[f"{tag}_feats"], atol=3e-4, rtol=0)
