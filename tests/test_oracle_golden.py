@@ -180,3 +180,29 @@ def test_vit_l_geometries_are_pinned_to_the_reference(gold_vitl, tag, geom_name,
     xt = OT.preprocess_pil(u8, geom.image_resolution)
     assert sha(xt.numpy()) == gold_vitl[f"{tag}_pre_sha"].tobytes()
     np.testing.assert_allclose(OT.encode_image(sdt, xt).numpy(), gold_vitl[f"{tag}_feats"], atol=3e-4, rtol=0)
+
+
+def b16_inputs():
+    n, side = 16, 300
+    return np.concatenate([synthetic_images_u8(n // 2, side, seed=1234),
+                           synthetic_images_u8(n - n // 2, side, seed=1234, start=n // 2, smooth=True)])
+
+
+def test_headline_geometry_is_pinned_to_the_reference(gold_vitl):
+    """BASELINE.json configs[1] — the full ViT-B/16 tower (197 tokens, 12 blocks, width 768) with the shipped 20-class
+    text head: both restatements against the unmodified reference's features and x100 logits."""
+    import torch
+    from oracle import clip_oracle_torch as OT
+    geom = GEOMETRIES["ViT-B/16"]
+    sd = make_state_dict_np(geom, 0, with_text=False)
+    u8 = b16_inputs()
+    x = np.stack([O.clip_preprocess(im, geom.image_resolution) for im in u8])
+    assert sha(x) == gold_vitl["b16_pre_sha"].tobytes(), "preprocessing must be bit-exact"
+    tw = gold_vitl["b16_text_w"]
+    emb, logits, _ = O.score(O.encode_image(sd, x), sd["visual.proj"], tw, 100.0, 3)
+    np.testing.assert_allclose(emb, gold_vitl["b16_emb"], atol=5e-6, rtol=0)
+    np.testing.assert_allclose(logits, gold_vitl["b16_logits"], atol=5e-4, rtol=0)
+    sdt = OT.to_torch_state(sd)
+    _, logits_t, _ = OT.score(OT.encode_image(sdt, OT.preprocess_pil(u8, geom.image_resolution)), sdt["visual.proj"],
+                              torch.from_numpy(tw), 100.0, 3)
+    np.testing.assert_allclose(logits_t.numpy(), gold_vitl["b16_logits"], atol=5e-4, rtol=0)
