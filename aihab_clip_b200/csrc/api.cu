@@ -1004,6 +1004,19 @@ int aihab_score(const float* feats, int n, int D, const float* proj, int E, cons
   return 0;
 }
 
+int aihab_l2_normalize(const void* x, int in_dtype, int rows, int cols, float eps, void* y, int out_dtype, void* stream) {
+  if (rows < 0 || cols <= 0 || in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2 || !(eps >= 0.f))
+    return fail("aihab_l2_normalize: bad argument");
+  if (rows == 0) return 0;
+  if (x == nullptr || y == nullptr) return fail("aihab_l2_normalize: null buffer");
+  DeviceGuard guard(device_of(x));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const double bytes = static_cast<double>(rows) * cols * ((in_dtype == 0 ? 4 : 2) + (out_dtype == 0 ? 4 : 2));
+  ProfScope ps(PC_SCORE, bytes, s);
+  CKL(aihab::launch_l2norm_rows(x, in_dtype, y, out_dtype, rows, cols, eps, s));
+  return 0;
+}
+
 int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj16, int E, const float* text_w, int C,
                   float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx, float* topk_val,
                   void* stream) {

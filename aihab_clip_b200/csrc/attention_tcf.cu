@@ -135,7 +135,7 @@ attention_tcf_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && total_steps > 0) {
+    if (total_steps > 0) {  // whole warp, converged; one elected lane issues each tcgen05 instruction (ptx.cuh "_w")
       const uint32_t idesc_o = ptx::make_idesc_f16(BF16 ? 1 : 0, 128, 64, /*b_mn_major=*/1);
       // S(g) = Q(it) K_j^T into S buffer g & 1
       auto issue_s = [&](int g, int it, int j, int st, int ring) {
@@ -149,9 +149,9 @@ attention_tcf_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint64_t qd = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + OFF_Q + (it & 1) * SQ_BYTES));
         const uint64_t kd = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + OFF_KV + st * SKV_BYTES));
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + b * TM_S, qd + 2 * kk, kd + 2 * kk, idesc_s, kk != 0);
-        ptx::umma_commit(&bar_sfull[b]);
-        if (j == nb - 1) ptx::umma_commit(&bar_qfree[it & 1]);
+        for (int kk = 0; kk < 4; ++kk) ptx::umma_f16_w(tmem + b * TM_S, qd + 2 * kk, kd + 2 * kk, idesc_s, kk != 0);
+        ptx::umma_commit_w(&bar_sfull[b]);
+        if (j == nb - 1) ptx::umma_commit_w(&bar_qfree[it & 1]);
       };
       int it = 0, j = 0, st = 0, ring = 0;      // step g
       int itn = 0, jn = 0, stn = 0, ringn = 0;  // step g + 1
@@ -177,11 +177,11 @@ attention_tcf_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t v_base = ptx::smem_u32(smem + OFF_KV + st * SKV_BYTES + SK_BYTES);
         for (int t = 0; t < ksteps; ++t) {
           const uint64_t vd = ptx::make_mnmajor_sw128_desc(v_base + t * 2048);
-          ptx::umma_f16_ts(tmem + TM_O, tmem + b * TM_S + t * 8, vd, idesc_o, (j | t) != 0);  // A = P from TMEM
+          ptx::umma_f16_ts_w(tmem + TM_O, tmem + b * TM_S + t * 8, vd, idesc_o, (j | t) != 0);  // A = P from TMEM
         }
-        ptx::umma_commit(bar_o);
-        ptx::umma_commit(&bar_kvfree[st]);
-        ptx::umma_commit(&bar_pvdone[b]);
+        ptx::umma_commit_w(bar_o);
+        ptx::umma_commit_w(&bar_kvfree[st]);
+        ptx::umma_commit_w(&bar_pvdone[b]);
         advance(it, j, st, ring);
         advance(itn, jn, stn, ringn);
       }

@@ -2,7 +2,7 @@
 // One CTA per SM walks a static list of work items (image, head, 128-query tile):
 //   warp 0 (lane 0)  TMA producer : Q [128x64], K [Lk x 64], V [Lk x 64] of item i+1 land in the other smem stage
 //                                   while item i is in its softmax
-//   warp 1 (lane 0)  MMA issuer   : S(i+1) = Q K^T is issued into the other TMEM S buffer BEFORE it waits for P(i), so
+//   warp 1 (converged) MMA issuer : S(i+1) = Q K^T is issued into the other TMEM S buffer BEFORE it waits for P(i), so
 //                                   the softmax warps never wait for a QK^T; then O = P(i) V (V read as an MN-major
 //                                   operand straight from its [key][d] tile)
 //   warps 2..9       softmax      : two threads per query row; S is read from TMEM once (registers), row max exchanged
@@ -197,7 +197,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {  // the whole warp runs the loop (converged); one elected lane issues each tcgen05 instruction (ptx.cuh "_w")
       const uint32_t idesc_s = ptx::make_idesc_f16(BF16 ? 1 : 0, 128, Lk);
       const uint32_t idesc_o = ptx::make_idesc_f16(BF16 ? 1 : 0, 128, 64, /*b_mn_major=*/1);
       const int ksteps = Lk >> 4;
@@ -210,8 +210,8 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint64_t qd = ptx::make_kmajor_sw128_desc(st + ST_Q);
         const uint64_t kd = ptx::make_kmajor_sw128_desc(st + ST_K);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem + b * TM_S, qd + 2 * kk, kd + 2 * kk, idesc_s, kk != 0);
-        ptx::umma_commit(&bar_sfull[b]);
+        for (int kk = 0; kk < 4; ++kk) ptx::umma_f16_w(tmem + b * TM_S, qd + 2 * kk, kd + 2 * kk, idesc_s, kk != 0);
+        ptx::umma_commit_w(&bar_sfull[b]);
       };
       if (n_items > 0) issue_s(0);
       for (int it = 0; it < n_items; ++it) {
@@ -223,11 +223,11 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t v_base = ptx::smem_u32(smem + s * ST_BYTES + ST_V);
         for (int j = 0; j < ksteps; ++j) {
           const uint64_t vd = ptx::make_mnmajor_sw128_desc(v_base + j * 2048);
-          ptx::umma_f16_ts(tmem + TM_O, tmem + b * TM_S + j * 8, vd, idesc_o, j != 0);  // A = P from TMEM
+          ptx::umma_f16_ts_w(tmem + TM_O, tmem + b * TM_S + j * 8, vd, idesc_o, j != 0);  // A = P from TMEM
         }
-        ptx::umma_commit(bar_o);
-        ptx::umma_commit(&bar_stfree[s]);
-        ptx::umma_commit(&bar_pvdone[b]);
+        ptx::umma_commit_w(bar_o);
+        ptx::umma_commit_w(&bar_stfree[s]);
+        ptx::umma_commit_w(&bar_pvdone[b]);
       }
     }
   } else {

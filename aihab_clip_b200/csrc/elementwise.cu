@@ -1,6 +1,8 @@
 // HBM-bound kernels of the hot path: LayerNorm, im2col, weight cast.  128-bit loads/stores, one warp per row.
 #include "kernels.cuh"
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdlib>
 #include "ptx.cuh"
@@ -191,6 +193,72 @@ __global__ void __launch_bounds__(128) eot_gather_kernel(const int64_t* __restri
   for (int c = lane; c < (D >> 2); c += 32) dst[c] = src[c];
 }
 
+
+template <int CODE> struct ElemOf;
+template <> struct ElemOf<0> { using type = float; };
+template <> struct ElemOf<1> { using type = __half; };
+template <> struct ElemOf<2> { using type = __nv_bfloat16; };
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Row L2 normalisation for any of fp32 / fp16 / bf16 in and out: y = x / max(||x||_2, eps), statistics in fp32
+// (F.normalize, methods/utils.py:184, aihab_utils/feature_cache.py:127; eps = 0 gives the `f /= f.norm()` variant of
+// utils.py:69, NaN rows for zero vectors included).  One warp per row; 16-byte loads and stores when the row pitch
+// allows it (cols % (16 / element size) == 0 and aligned bases), element-wise otherwise.
+template <int IN, int OUT>  // 0 = fp32, 1 = fp16, 2 = bf16
+__global__ void __launch_bounds__(128) l2norm_rows_kernel(const void* __restrict__ xin, void* __restrict__ yout, int rows,
+                                                          int cols, float eps, int vec) {
+  using TI = typename ElemOf<IN>::type;
+  using TO = typename ElemOf<OUT>::type;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const TI* src = static_cast<const TI*>(xin) + static_cast<size_t>(row) * cols;
+  TO* dst = static_cast<TO*>(yout) + static_cast<size_t>(row) * cols;
+  constexpr int VI = 16 / sizeof(TI);  // elements per 16-byte load
+  float s = 0.f;
+  if (vec) {
+    for (int c = lane * VI; c < cols; c += 32 * VI) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + c);
+      const TI* e = reinterpret_cast<const TI*>(&raw);
+#pragma unroll
+      for (int j = 0; j < VI; ++j) {
+        const float f = to_float(e[j]);
+        s = fmaf(f, f, s);
+      }
+    }
+  } else {
+    for (int c = lane; c < cols; c += 32) {
+      const float f = to_float(src[c]);
+      s = fmaf(f, f, s);
+    }
+  }
+  const float inv_denom_src = fmaxf(sqrtf(warp_sum(s)), eps);
+  if (vec) {
+    for (int c = lane * VI; c < cols; c += 32 * VI) {  // second read of the row hits L1/L2
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + c);
+      const TI* e = reinterpret_cast<const TI*>(&raw);
+      TO o[VI];
+#pragma unroll
+      for (int j = 0; j < VI; ++j) o[j] = from_float<TO>(to_float(e[j]) / inv_denom_src);
+      constexpr int NV = VI * sizeof(TO) / 16 > 0 ? VI * sizeof(TO) / 16 : 1;
+      if constexpr (VI * sizeof(TO) >= 16) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) reinterpret_cast<uint4*>(dst + c)[q] = reinterpret_cast<const uint4*>(o)[q];
+      } else {  // fp32 in, 16-bit out: 4 elements = 8 bytes
+        *reinterpret_cast<uint2*>(dst + c) = *reinterpret_cast<const uint2*>(o);
+      }
+    }
+  } else {
+    for (int c = lane; c < cols; c += 32) dst[c] = from_float<TO>(to_float(src[c]) / inv_denom_src);
+  }
+}
+
 }  // namespace
 
 bool pdl_enabled() {
@@ -262,6 +330,32 @@ cudaError_t launch_eot_gather(const int64_t* tokens, const float* x, float* out,
   if (n <= 0) return cudaSuccess;
   if ((D & 3) != 0) return cudaErrorInvalidValue;
   eot_gather_kernel<<<(n + 3) / 4, 128, 0, stream>>>(tokens, x, out, n, L, D);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_l2norm_rows(const void* x, int in_dtype, void* y, int out_dtype, int rows, int cols, float eps,
+                               cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (cols <= 0 || in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2) return cudaErrorInvalidValue;
+  const int isz = in_dtype == 0 ? 4 : 2, osz = out_dtype == 0 ? 4 : 2;
+  const int vi = 16 / isz;
+  const int vec = (cols % vi == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
+                  (reinterpret_cast<uintptr_t>(y) % (vi * osz >= 16 ? 16 : 8) == 0) &&
+                  ((static_cast<size_t>(cols) * osz) % (vi * osz >= 16 ? 16 : 8) == 0);
+  const dim3 grid((rows + 3) / 4);
+#define AIHAB_L2N(I, O) l2norm_rows_kernel<I, O><<<grid, 128, 0, stream>>>(x, y, rows, cols, eps, vec)
+  switch (in_dtype * 3 + out_dtype) {
+    case 0: AIHAB_L2N(0, 0); break;
+    case 1: AIHAB_L2N(0, 1); break;
+    case 2: AIHAB_L2N(0, 2); break;
+    case 3: AIHAB_L2N(1, 0); break;
+    case 4: AIHAB_L2N(1, 1); break;
+    case 5: AIHAB_L2N(1, 2); break;
+    case 6: AIHAB_L2N(2, 0); break;
+    case 7: AIHAB_L2N(2, 1); break;
+    default: AIHAB_L2N(2, 2); break;
+  }
+#undef AIHAB_L2N
   return cudaGetLastError();
 }
 

@@ -194,8 +194,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {  // in a pair only the leader issues
+    // The WHOLE warp runs this loop (converged; one elected lane issues each tcgen05 instruction, ptx.cuh "_w"
+    // variants) so that the descriptors live in uniform registers and the four MMAs of a k-block issue back to back.
+    if (cta_rank == 0) {  // in a pair only the leader issues
       const uint32_t idesc = ptx::make_idesc_f16(p.ab_format, TWO ? 2 * BM : BM, BN);
+      const uint32_t sA_u32 = ptx::smem_u32(sA), sB_u32 = ptx::smem_u32(sB);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -208,22 +211,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint64_t adesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA + stage * L::kABytes));
-          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sB + stage * L::kBBytes));
+          const uint64_t adesc = ptx::make_kmajor_sw128_desc(sA_u32 + stage * L::kABytes);
+          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sB_u32 + stage * L::kBBytes);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 B (UMMA_K x 2 B) inside the 128 B swizzle row: +2 in the (addr >> 4) field
             if constexpr (TWO)
-              ptx::umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              ptx::umma_f16_pair_w(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
             else
-              ptx::umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              ptx::umma_f16_w(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           if constexpr (TWO) {
-            ptx::umma_commit_pair(&empty_bar[stage]);  // frees this smem slot in both CTAs
-            if (kb == num_kb - 1) ptx::umma_commit_pair(&tmem_full_bar[as]);
+            ptx::umma_commit_pair_w(&empty_bar[stage]);  // frees this smem slot in both CTAs
+            if (kb == num_kb - 1) ptx::umma_commit_pair_w(&tmem_full_bar[as]);
           } else {
-            ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-            if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[as]);
+            ptx::umma_commit_w(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+            if (kb == num_kb - 1) ptx::umma_commit_w(&tmem_full_bar[as]);
           }
           if (++stage == kStages) {
             stage = 0;

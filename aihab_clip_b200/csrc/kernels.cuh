@@ -109,6 +109,10 @@ cudaError_t launch_sgemm(const float* A, const float* B, float* C, int M, int N,
                          cudaStream_t stream);
 // rows / max(||row||_2, eps)   (F.normalize, eps 1e-12); in place allowed.
 cudaError_t launch_l2norm(const float* x, float* y, int rows, int cols, float eps, cudaStream_t stream);
+// Same for rows of any dtype (0 = fp32, 1 = fp16, 2 = bf16) in and out, 128-bit loads/stores; eps = 0 reproduces
+// `f /= f.norm(dim=-1, keepdim=True)` (utils.py:69).  The feature-cache writers normalise with it in the model dtype.
+cudaError_t launch_l2norm_rows(const void* x, int in_dtype, void* y, int out_dtype, int rows, int cols, float eps,
+                               cudaStream_t stream);
 // top-k per row, descending, lowest index first among exact ties (torch.topk / argmax semantics). k <= 16.
 cudaError_t launch_topk(const float* logits, int rows, int cols, int k, int64_t* idx, float* val,
                         cudaStream_t stream);

@@ -168,6 +168,13 @@ AIHAB_API int aihab_preprocess_u8(const uint8_t* images_u8, int n, int sh, int s
 AIHAB_API int aihab_score(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C, float scale,
                 int k, float* emb_out, float* logits_out, int64_t* topk_idx, float* topk_val, void* stream);
 
+/* Row L2 normalisation y = x / max(||x||_2, eps) for rows of fp32 / fp16 / bf16 (dtype codes as above), fp32
+ * statistics, in place allowed when the dtypes match.  Replaces F.normalize(feats, dim=-1) in the cache writers
+ * (aihab_utils/feature_cache.py:126-127, methods/utils.py:39, eps = 1e-12) and, with eps = 0,
+ * `image_features /= image_features.norm(dim=-1, keepdim=True)` (utils.py:69). */
+AIHAB_API int aihab_l2_normalize(const void* x, int in_dtype, int rows, int cols, float eps, void* y, int out_dtype,
+                                 void* stream);
+
 /* Same scoring over CACHED 16-bit features on the tensor cores (ProLIP / linear-probe scoring over a feature cache,
  * methods/ProLIP.py:288-293; the reference caches features in the model dtype, fp16 on GPU — feature_cache.py:215).
  *   feats16 : [n, D] fp16/bf16 (dtype)          proj16 : [D, E] same dtype (visual.proj after convert_weights)

@@ -33,6 +33,12 @@ def gold_vitl():
 
 
 @pytest.fixture(scope="session")
+def gold_full():
+    """Reference outputs at FULL depth for BASELINE.json configs 1, 3, 4 (tests/golden/make_golden_full.py)."""
+    return np.load(GOLDEN / "reference_outputs_full.npz")
+
+
+@pytest.fixture(scope="session")
 def meta():
     return json.loads((GOLDEN / "reference_meta.json").read_text())
 

@@ -170,7 +170,7 @@ def test_zero_shot_agreement_on_4096_images(tmp_path, cuda_device, gold, capsys)
               f"{agree[~near_tie].mean() * 100:.3f}% disagreements among untied={int((~agree[~near_tie]).sum())}")
     assert err <= 1e-2
     assert agree[~near_tie].all(), "an untied zero-shot prediction differs from the reference"
-    assert agree.mean() >= 0.999 or (~agree).sum() <= near_tie.sum()
+    assert agree.mean() >= 0.999  # BASELINE.json gate, strict (near-ties included)
     untied3 = np.abs(np.diff(srt[:, :4], axis=1)).min(axis=1) > 2 * err
     np.testing.assert_array_equal(idx.cpu().numpy()[untied3], np.argsort(-ref, axis=1, kind="stable")[untied3, :3])
 

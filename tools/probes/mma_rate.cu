@@ -14,11 +14,25 @@
 #include "ptx.cuh"
 
 
+// issue by a CONVERGED warp: every lane computes the (uniform) descriptors, one elected lane issues.  The compiler can
+// then keep the operands in uniform registers instead of the R2UR.BROADCAST + ELECT waterfall it emits around a
+// tcgen05.mma sitting in a divergent `if (lane == 0)` region.
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 constexpr int THREADS = 192;  // warp 0: issuer, warp 1: TMEM allocator, warps 2..5: optional smem traffic
 constexpr int SMEM = 200 * 1024;
 
 __global__ void __launch_bounds__(THREADS, 1)
-probe(int n, int ts, int reps, int traffic, long long* cycles_out) {
+probe(int n, int ts, int reps, int traffic, long long* cycles_out, int mode = 0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar;
@@ -38,17 +52,49 @@ probe(int n, int ts, int reps, int traffic, long long* cycles_out) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (warp == 0) {
+  if (warp == 0 && mode == 4) {  // converged-warp issue, k walk, one accumulator (compare with the base case)
+    const uint64_t adesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
+    const uint64_t bdesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + 16384));
+    const uint32_t idesc = ptx::make_idesc_f16(0, 128, n, 0);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      const int k = r & 3;
+      umma_f16_elect(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, r != 0);
+    }
+    if (lane == 0) {
+      ptx::umma_commit(&bar);
+      ptx::mbar_wait(&bar, 0);
+      cycles_out[blockIdx.x] = clock64() - t0;
+      stop = 1;
+    }
+    __syncwarp();
+  } else if (warp == 0) {
     if (lane == 0) {
       // A tile: 128 rows x 64 (K-major, SW128) at smem + 0; B tile: up to 256 rows x 64 at smem + 16 KB
       const uint64_t adesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
       const uint64_t bdesc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + 16384));
       const uint32_t idesc = ptx::make_idesc_f16(0, 128, n, ts ? 1 : 0);
       const long long t0 = clock64();
+      if (mode == 1) {         // two accumulators, alternating: is it the dependent accumulate into ONE D tile?
+        for (int r = 0; r < reps; ++r) {
+          const int k = r & 3;
+          ptx::umma_f16(tmem + ((r >> 2) & 1) * 256, adesc + 2 * k, bdesc + 2 * k, idesc, r > 7);
+        }
+      } else if (mode == 2) {  // issue loop unrolled by 4, constant predicate: is it the issuing thread?
+        for (int r = 0; r < reps; r += 4) {
+          ptx::umma_f16(tmem, adesc + 0, bdesc + 0, idesc, 1);
+          ptx::umma_f16(tmem, adesc + 2, bdesc + 2, idesc, 1);
+          ptx::umma_f16(tmem, adesc + 4, bdesc + 4, idesc, 1);
+          ptx::umma_f16(tmem, adesc + 6, bdesc + 6, idesc, 1);
+        }
+      } else if (mode == 3) {  // same operands every time (no k walk): is it the operand fetch?
+        for (int r = 0; r < reps; ++r) ptx::umma_f16(tmem, adesc, bdesc, idesc, 1);
+      } else {
       for (int r = 0; r < reps; ++r) {
         const int k = r & 3;  // walk the four K = 16 slices of the 64-wide tile like the real kernels
-        if (ts) ptx::umma_f16_ts(tmem + 256, tmem + 8 * k, bdesc + 2 * k, idesc, r != 0);  // A = TMEM cols, D at col 256
+        if (ts) ptx::umma_f16_ts(ts == 2 ? tmem : tmem + 256, tmem + (ts == 2 ? 256 : 0) + 8 * k, bdesc + 2 * k, idesc, r != 0);  // A = TMEM cols
         else ptx::umma_f16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, r != 0);
+      }
       }
       ptx::umma_commit(&bar);
       ptx::mbar_wait(&bar, 0);
@@ -107,6 +153,25 @@ int main() {
       const char* tn[] = {"alone", "+ st.shared", "+ ld.shared", "+ st/ld.shared"};
       printf("%s  %-15s %7.1f cycles/MMA   (full rate would be %d)\n", c.name, tn[traffic], s / sms / reps, c.n / 2);
     }
+  }
+  struct Extra { const char* name; int n, ts, mode; };
+  const Extra extra[] = {{"SS M128 N256 two accumulators alternating", 256, 0, 1}, {"SS M128 N256 issue unrolled x4", 256, 0, 2},
+                         {"SS M128 N256 same operand slice", 256, 0, 3},          {"TS M128 N256 (A from TMEM)", 256, 2, 0},
+                         {"SS M128 N256 converged warp + elect, k walk", 256, 0, 4}, {"SS M128 N128 converged warp + elect, k walk", 128, 0, 4},
+                         {"SS M128 N128 issue unrolled x4", 128, 0, 2},           {"SS M128 N64 issue unrolled x4", 64, 0, 2}};
+  for (const Extra& c : extra) {
+    for (int rep = 0; rep < 2; ++rep) {
+      probe<<<sms, THREADS, SMEM>>>(c.n, c.ts, reps, 0, d, c.mode);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) {
+        printf("%s: %s\n", c.name, cudaGetErrorString(e));
+        return 1;
+      }
+    }
+    cudaMemcpy(h, d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+    double s = 0;
+    for (int i = 0; i < sms; ++i) s += h[i];
+    printf("%-45s %7.1f cycles/MMA   (nominal floor %d)\n", c.name, s / sms / reps, c.n / 2);
   }
   return 0;
 }
