@@ -309,7 +309,7 @@ struct aihab_vit {
   void* y = nullptr;        // [cap_rows, D] 16-bit (LN output / attention output)
   void* big = nullptr;      // [cap_rows, 4D] 16-bit (qkv [.,3D] and MLP hidden [.,4D] share it)
   void* y2 = nullptr;       // [cap_rows, D] 16-bit: gamma * x written by the residual epilogues (LayerNorm fold)
-  float* ln_stats = nullptr;  // [cap_rows, kMaxStatBlocks, 2] per-tile (sum, sum sq) partials of the residual rows
+  float* ln_stats = nullptr;  // [cap_rows, kMaxStatBlocks, 2] per 128-column block (mean, sum of squared deviations) of the residual rows
   bool ln_fold = true;
   bool zigzag = true;  // consecutive kernels walk the rows in opposite directions (L2 keeps the producer's last rows)
   CUtensorMap m_y2;

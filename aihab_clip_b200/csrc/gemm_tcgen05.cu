@@ -33,7 +33,8 @@ __host__ __device__ constexpr int epi_warps(int epi, bool two) {
 __host__ __device__ constexpr int num_threads(int epi, bool two) { return (EPI_WARP0 + epi_warps(epi, two)) * 32; }
 
 constexpr int RES_BOX = 32 * 128;  // 32 rows x 32 fp32 = 4 KB TMA box, SWIZZLE_128B
-constexpr int STAT_COLS = 128;     // LayerNorm producer: one (sum, sum of squares) partial per row and 128 columns
+constexpr int STAT_COLS = 128;     // LayerNorm producer: one (mean, sum of squared deviations) partial per row and 128 columns
+constexpr int kMaxStatBlocks = 8;  // width <= 1024 (api.cu allocates the statistics buffer with the same bound)
 
 template <int BN, int EPI, bool TWO>
 struct SmemLayout {
@@ -314,15 +315,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int grow = m0 + lane;
         if (grow < p.M) {
           const float* st = p.ln_stats + static_cast<size_t>(grow) * p.ln_nsb * 2;
-          float s1 = 0.f, s2 = 0.f;
-          for (int b = 0; b < p.ln_nsb; ++b) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(st) + b);
-            s1 += v.x;
-            s2 += v.y;
+          // per 128-column block the producer left (block mean, sum of squared deviations from it), both computed
+          // around a pivot inside the block; merged here with the parallel-variance formula (Chan et al.): no
+          // E[x^2] - mu^2 cancellation, whatever common offset or outlier channels the residual stream carries
+          float2 sv[kMaxStatBlocks];
+          float msum = 0.f;
+#pragma unroll
+          for (int b = 0; b < kMaxStatBlocks; ++b) {
+            if (b < p.ln_nsb) {
+              sv[b] = __ldg(reinterpret_cast<const float2*>(st) + b);
+              msum += sv[b].x;
+            }
           }
-          const float inv_k = 1.0f / static_cast<float>(p.K);
-          const float mu = s1 * inv_k;
-          const float var = fmaxf(fmaf(-mu, mu, s2 * inv_k), 0.0f);
+          const float mu = msum / static_cast<float>(p.ln_nsb);
+          float m2 = 0.f;
+#pragma unroll
+          for (int b = 0; b < kMaxStatBlocks; ++b) {
+            if (b < p.ln_nsb) {
+              const float d = sv[b].x - mu;
+              m2 += fmaf(static_cast<float>(STAT_COLS) * d, d, sv[b].y);
+            }
+          }
+          const float var = fmaxf(m2 / static_cast<float>(p.K), 0.0f);
           ln_r = rsqrtf(var + 1e-5f);
           ln_nrm = -ln_r * mu;
         }
@@ -395,7 +409,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
       } else if constexpr (EPI == EPI_BIAS_RES_32) {
-        float ln_s1 = 0.f, ln_s2 = 0.f;  // LayerNorm producer: this row's sum / sum of squares over the tile
+        float ln_s1 = 0.f, ln_s2 = 0.f, ln_piv = 0.f;  // LayerNorm producer: this row's pivoted sum / sum of squares over a 128-column block
         const int prow = m0 + lane;
 #pragma unroll 1
         for (int cl = 0; cl < CPT; ++cl, ++q) {
@@ -420,11 +434,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             v.w += __uint_as_float(r[4 * u + 3]) + b4.w;
             xv[u] = v;
             if (ln_prod) {  // reuse r[] for the packed gamma * x_new row segment
-              ln_s1 += (v.x + v.y) + (v.z + v.w);
-              ln_s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ln_s2))));
+              // statistics around a pivot (the block's first element): sums of small deviations, no cancellation
+              if (u == 0 && (c & (STAT_COLS / 32 - 1)) == 0) ln_piv = v.x;
+              const float dx = v.x - ln_piv, dy = v.y - ln_piv, dz = v.z - ln_piv, dw = v.w - ln_piv;
+              ln_s1 += (dx + dy) + (dz + dw);
+              ln_s2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, ln_s2))));
               const float4 g4 = *reinterpret_cast<const float4*>(sx + c * 32 + 4 * u);
-              r[2 * u] = bf16 ? ptx::pack2<true>(g4.x * v.x, g4.y * v.y) : ptx::pack2<false>(g4.x * v.x, g4.y * v.y);
-              r[2 * u + 1] = bf16 ? ptx::pack2<true>(g4.z * v.z, g4.w * v.w) : ptx::pack2<false>(g4.z * v.z, g4.w * v.w);
+              r[2 * u] = bf16 ? ptx::pack2_sat<true>(g4.x * v.x, g4.y * v.y) : ptx::pack2_sat<false>(g4.x * v.x, g4.y * v.y);
+              r[2 * u + 1] = bf16 ? ptx::pack2_sat<true>(g4.z * v.z, g4.w * v.w) : ptx::pack2_sat<false>(g4.z * v.z, g4.w * v.w);
             }
           }
 #pragma unroll
@@ -464,7 +481,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int sblk = (n0 + c * 32) / STAT_COLS;
             if (prow < p.M && sblk * STAT_COLS < p.N)
               *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(prow) * ((p.N + STAT_COLS - 1) / STAT_COLS) + sblk) * 2) =
-                  make_float2(ln_s1, ln_s2);
+                  make_float2(fmaf(ln_s1, 1.0f / STAT_COLS, ln_piv), fmaf(-ln_s1 * (1.0f / STAT_COLS), ln_s1, ln_s2));
             ln_s1 = ln_s2 = 0.f;
           }
         }

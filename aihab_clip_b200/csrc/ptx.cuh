@@ -387,6 +387,19 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
   }
 }
+// same, saturating to the largest finite value instead of overflowing to +-inf (one F2FP.SATFINITE either way): for
+// operands that are NOT normalised yet (the gamma * x rows of the LayerNorm fold), where an outlier channel of a
+// pretrained checkpoint must not poison the row with inf - inf = NaN
+template <bool IS_BF16>
+__device__ __forceinline__ uint32_t pack2_sat(float lo, float hi) {
+  uint32_t r;
+  if constexpr (IS_BF16) {
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  }
+  return r;
+}
 template <bool IS_BF16>
 __device__ __forceinline__ float2 unpack2(uint32_t u) {
   if constexpr (IS_BF16) {

@@ -71,6 +71,8 @@ class ShardedExtractor:
         self.copy_results_to_host = copy_results_to_host
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.last_compute_ms = 0.0   # device time of this rank's shard in the last run() (before the gather)
+        self.last_gather_ms = 0.0    # device time of the single all-gather in the last run()
         # step_fn(images) -> (emb [n,E] fp32, idx [n,1] int64) replaces the CUDA path; it exists so that the
         # sharding / packing / gather logic can be exercised by world_size-2 gloo tests on a CPU-only box
         self._step_fn = step_fn
@@ -136,6 +138,8 @@ class ShardedExtractor:
             self.h2d_bytes += src.numel() * src.element_size()
             return d, ev
 
+        t_begin, t_shard, t_gathered = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        t_begin.record(compute)
         nxt = stage(0) if starts else None
         for i, b0 in enumerate(starts):
             cur, ev = nxt
@@ -156,13 +160,22 @@ class ShardedExtractor:
                     host_out[row0:row0 + n].copy_(packed[row0:row0 + n], non_blocking=True)
                 self.d2h_bytes += n * (E + 1) * 4
         if host_out is not None:
-            compute.wait_stream(self._out_stream)
+            # the caller reads host_copy on the CPU: the HOST must wait for the last device->host copy, not only the
+            # compute stream.  The pinned buffer is cached and re-used by the next run(): copy it before that.
+            done_out = torch.cuda.Event()
+            done_out.record(self._out_stream)
+            done_out.synchronize()
+        t_shard.record(compute)
         if gather and self.world > 1:
             if self.dist is None:
                 raise RuntimeError("world_size > 1 needs an initialised torch.distributed process group")
             full = self._gather(packed, per, n_total)
         else:
             full = packed[:hi - lo]
+        t_gathered.record(compute)
+        t_gathered.synchronize()
+        self.last_compute_ms = t_begin.elapsed_time(t_shard)
+        self.last_gather_ms = t_shard.elapsed_time(t_gathered)
         return {"features": full[:, :E], "preds": full[:, E].to(torch.int64), "host_copy": host_out,
                 "range": (lo, hi)}
 
@@ -173,3 +186,294 @@ def array_source(images, pin: bool = True) -> Callable[[int, int], torch.Tensor]
     if pin and not t.is_cuda and torch.cuda.is_available():
         t = t.pin_memory()
     return lambda lo, hi: t[lo:hi]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Loader-driven extraction: the loops of methods/utils.py:142-173, aihab_utils/feature_cache.py:114-142,
+# utils.py:60-82 and methods/utils.py:31-45, sharded BY IMAGE BATCH across the ranks of one box.
+# ------------------------------------------------------------------------------------------------------------------
+def _dist_state(rank=None, world=None):
+    import torch.distributed as dist
+    d = dist if (dist.is_available() and dist.is_initialized()) else None
+    r = rank if rank is not None else (d.get_rank() if d else 0)
+    w = world if world is not None else (d.get_world_size() if d else 1)
+    if w > 1 and d is None:
+        raise RuntimeError("world_size > 1 needs an initialised torch.distributed process group")
+    return d, r, w
+
+
+def _split_batch(batch):
+    """(images, targets) or (images, targets, metadata) — the two batch forms of the reference loaders
+    (aihab_utils/feature_cache.py:116-122)."""
+    if isinstance(batch, (list, tuple)) and len(batch) == 3:
+        return batch[0], batch[1], batch[2]
+    if isinstance(batch, (list, tuple)) and len(batch) == 2:
+        return batch[0], batch[1], None
+    raise ValueError("Expected batch to be (images, targets) or (images, targets, metadata).")
+
+
+def _index_batches(loader):
+    """Index batches of a torch DataLoader over a map-style dataset, or None when the loader is any other iterable."""
+    from torch.utils.data import DataLoader, IterableDataset
+    if not isinstance(loader, DataLoader) or isinstance(loader.dataset, IterableDataset):
+        return None
+    if getattr(loader, "batch_sampler", None) is None:
+        return None
+    # consume the RNG exactly as `for batch in loader` would (so a shuffling loader yields the order the reference's
+    # single pass would see): DataLoader's iterator draws its base seed from loader.generator before the sampler
+    # draws its permutation (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__)
+    torch.empty((), dtype=torch.int64).random_(generator=loader.generator)
+    return [list(map(int, b)) for b in loader.batch_sampler]
+
+
+class LoaderShards:
+    """Which rank encodes which batch of a loader, and how the gathered rows map back to loader order.
+
+    * ``index`` mode (torch DataLoader over a map-style dataset): rank 0 draws the index batches ONCE from the
+      loader's batch sampler (so a shuffling sampler consumes its RNG exactly as in the reference's single pass) and
+      broadcasts them; rank r then loads and encodes the contiguous block ``shard_range(n_batches, r, G)`` of batches
+      through a private DataLoader over the same dataset / collate_fn — no rank decodes another rank's images.
+    * ``iter`` mode (any other iterable of batches): every rank walks the whole iterable and encodes batch b only
+      when ``b % G == rank``; the other batches' images are never moved to the device.
+    """
+
+    def __init__(self, loader, rank: int, world: int, dist=None):
+        self.loader, self.rank, self.world, self.dist = loader, rank, world, dist
+        self.mode = "all"
+        self.index_batches = None
+        self.sizes: list = []    # rows of every batch, loader order
+        self.owner: list = []    # encoding rank of every batch
+        if world > 1:
+            box = [_index_batches(loader) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self.index_batches = box[0]
+            self.mode = "index" if self.index_batches is not None else "iter"
+            if self.mode == "index":
+                nb = len(self.index_batches)
+                self.sizes = [len(b) for b in self.index_batches]
+                self.owner = [0] * nb
+                for r in range(world):
+                    lo, hi, _ = shard_range(nb, r, world)
+                    for b in range(lo, hi):
+                        self.owner[b] = r
+
+    def __iter__(self):
+        """Yields (batch_index, batch) for the batches THIS rank encodes; fills sizes / owner in iter mode."""
+        if self.mode == "all":
+            for b, batch in enumerate(self.loader):
+                self.owner.append(0)
+                yield b, batch
+        elif self.mode == "index":
+            from torch.utils.data import DataLoader
+            lo, hi, _ = shard_range(len(self.index_batches), self.rank, self.world)
+            if hi > lo:
+                ld = self.loader
+                sub = DataLoader(ld.dataset, batch_sampler=self.index_batches[lo:hi], collate_fn=ld.collate_fn,
+                                 num_workers=ld.num_workers, pin_memory=ld.pin_memory)
+                for i, batch in enumerate(sub):
+                    yield lo + i, batch
+        else:
+            for b, batch in enumerate(self.loader):
+                self.owner.append(b % self.world)
+                self.sizes.append(int(_split_batch(batch)[1].shape[0]))
+                if b % self.world == self.rank:
+                    yield b, batch
+
+    def note_size(self, n: int):
+        if self.mode == "all":
+            self.sizes.append(int(n))
+
+    def gather_index(self, per: int) -> torch.Tensor:
+        """int64 [N]: position of every loader-order row inside the all-gathered ``[world * per, ...]`` buffer."""
+        offs = [0] * self.world
+        idx = []
+        for n, r in zip(self.sizes, self.owner):
+            idx.append(torch.arange(r * per + offs[r], r * per + offs[r] + n, dtype=torch.int64))
+            offs[r] += n
+        return torch.cat(idx) if idx else torch.zeros(0, dtype=torch.int64)
+
+    def local_rows(self, rank: int) -> int:
+        return sum(n for n, r in zip(self.sizes, self.owner) if r == rank)
+
+
+def _default_encode(model, images: torch.Tensor) -> torch.Tensor:
+    if images.dtype == torch.uint8:  # raw HWC batch: GPU preprocessing fused in front of the tower
+        return model.encode_image_u8(images)
+    return model.encode_image(images)
+
+
+def extract_loader(model, loader, *, post_fn: Optional[Callable] = None, to_cpu: bool = False,
+                   want_metadata: bool = False, device=None, rank: Optional[int] = None,
+                   world_size: Optional[int] = None, encode_fn: Optional[Callable] = None,
+                   spill_bytes: Optional[int] = None):
+    """One pass over ``loader`` -> (features [N, W], labels [N] int64, metadata rows | None), loader order, identical
+    on every rank.
+
+    Per batch (on the rank that owns it): host->device copy on a side stream (prefetched one batch ahead) ->
+    ``encode_image`` (``encode_image_u8`` for raw uint8 HWC batches) -> ``post_fn`` (normalise / project / score, on
+    the device).  Rows accumulate in HBM: there is NO per-batch ``.to('cpu')`` synchronisation (the reference syncs
+    every batch, methods/utils.py:164).  With G > 1 ranks the shards meet in ONE ``all_gather_into_tensor`` of byte
+    rows ``[features | int64 label]``; ``to_cpu`` ends with ONE device->host copy through pinned memory.
+    ``encode_fn(images) -> features`` replaces the CUDA path in the world_size-2 gloo tests of this logic.
+    """
+    import os
+    dist, rank, world = _dist_state(rank, world_size)
+    if device is None:
+        try:
+            device = next(model.parameters()).device
+        except (StopIteration, AttributeError):
+            device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+    device = torch.device(device)
+    on_cuda = device.type == "cuda"
+    if not on_cuda and encode_fn is None:
+        raise RuntimeError("feature extraction needs the model on a CUDA device (no CPU fallback)")
+    encode = encode_fn if encode_fn is not None else (lambda im: _default_encode(model, im))
+    if spill_bytes is None:
+        spill_bytes = int(os.environ.get("AIHAB_CACHE_SPILL_MB", "8192")) << 20
+    shards = LoaderShards(loader, rank, world, dist)
+    copy_stream = torch.cuda.Stream(device) if on_cuda else None
+    compute = torch.cuda.current_stream(device) if on_cuda else None
+
+    def stage(item):
+        b, batch = item
+        images, targets, metadata = _split_batch(batch)
+        if on_cuda and not images.is_cuda:
+            with torch.cuda.stream(copy_stream):
+                d = images.to(device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return b, d, ev, targets, metadata
+        return b, images, None, targets, metadata
+
+    feats, labels, rows = [], [], []
+    host_chunks, acc_bytes = [], 0
+    it = iter(shards)
+    nxt = next(it, None)
+    nxt = stage(nxt) if nxt is not None else None
+    with torch.no_grad():
+        while nxt is not None:
+            b, images, ev, targets, metadata = nxt
+            following = next(it, None)
+            nxt = stage(following) if following is not None else None  # copy of batch b+1 overlaps compute of batch b
+            if ev is not None:
+                compute.wait_event(ev)
+            f = encode(images)
+            if on_cuda and images.is_cuda:
+                images.record_stream(compute)
+            if post_fn is not None:
+                f = post_fn(f)
+            feats.append(f)
+            shards.note_size(f.shape[0])
+            labels.append(targets.detach().reshape(-1).to(torch.int64))
+            if want_metadata:
+                rows.extend(metadata_rows(metadata, int(f.shape[0])))
+            acc_bytes += f.numel() * f.element_size()
+            if to_cpu and world == 1 and on_cuda and acc_bytes >= spill_bytes:
+                # bound the HBM held by a very large pass (the reason the reference has to_cpu at all): spill the
+                # accumulated block to pinned host memory asynchronously and go on
+                blk = torch.cat(feats, dim=0)
+                host = torch.empty(blk.shape, dtype=blk.dtype, pin_memory=True)
+                host.copy_(blk, non_blocking=True)
+                host_chunks.append(host)
+                feats, acc_bytes = [], 0
+    width_probe = feats[0] if feats else (host_chunks[0] if host_chunks else None)
+    if width_probe is None and world == 1:
+        return torch.zeros(0, 0), torch.zeros(0, dtype=torch.int64), ([] if want_metadata else None)
+    lab_local = torch.cat(labels) if labels else torch.zeros(0, dtype=torch.int64)
+
+    if world == 1:
+        x = torch.cat(feats, dim=0) if feats else None
+        if to_cpu:
+            if x is not None and x.is_cuda:
+                host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+                host.copy_(x, non_blocking=True)       # the ONE device->host copy of the pass
+                torch.cuda.current_stream(device).synchronize()
+                host_chunks.append(host)
+            elif x is not None:
+                host_chunks.append(x)
+            x = host_chunks[0] if len(host_chunks) == 1 else torch.cat(host_chunks, dim=0)
+            y = lab_local.cpu()
+        else:
+            y = lab_local.to(device, non_blocking=True)
+        return x, y, (rows if want_metadata else None)
+
+    # ---- G > 1: one all-gather of byte rows [features | label]
+    info = [None]
+    if feats:
+        info[0] = (int(feats[0].shape[1]), str(feats[0].dtype))
+    all_info = [None] * world
+    if shards.mode == "index" and want_metadata:
+        all_rows = [None] * world
+        dist.all_gather_object(all_rows, (info[0], rows))   # host-side strings; not a data-path collective
+        all_info = [a[0] for a in all_rows]
+    else:
+        dist.all_gather_object(all_info, info[0])
+    if all(a is None for a in all_info):   # an empty loader
+        return torch.zeros(0, 0), torch.zeros(0, dtype=torch.int64), ([] if want_metadata else None)
+    W, dt_name = next(a for a in all_info if a is not None)
+    dt = getattr(torch, dt_name.replace("torch.", ""))
+    isz = torch.empty(0, dtype=dt).element_size()
+    per = max(shards.local_rows(r) for r in range(world))
+    rowb = W * isz + 8
+    payload = torch.zeros(per, rowb, dtype=torch.uint8, device=device)
+    n_loc = shards.local_rows(rank)
+    if n_loc:
+        x = torch.cat(feats, dim=0).contiguous()
+        payload[:n_loc, :W * isz] = x.view(torch.uint8).reshape(n_loc, W * isz)
+        payload[:n_loc, W * isz:] = lab_local.to(device).contiguous().view(torch.uint8).reshape(n_loc, 8)
+    full = torch.empty(world * per, rowb, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(full, payload)   # the ONLY data-path collective (NCCL over NVLink)
+    sel = full.index_select(0, shards.gather_index(per).to(device))
+    N = sel.shape[0]
+    x = sel[:, :W * isz].contiguous().view(dt).reshape(N, W)
+    y = sel[:, W * isz:].contiguous().view(torch.int64).reshape(N)
+    if to_cpu:
+        if x.is_cuda:
+            host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+            host.copy_(x, non_blocking=True)
+            hy = y.to("cpu", non_blocking=False)
+            torch.cuda.current_stream(device).synchronize()
+            x, y = host, hy
+        else:
+            x, y = x.cpu(), y.cpu()
+    meta_rows = None
+    if want_metadata:
+        if shards.mode == "index":
+            per_rank = [list(a[1]) for a in all_rows]
+            pos = [0] * world
+            meta_rows = []
+            for n, r in zip(shards.sizes, shards.owner):
+                meta_rows.extend(per_rank[r][pos[r]:pos[r] + n])
+                pos[r] += n
+        else:   # iter mode: this rank saw every batch's metadata only for its own batches -> exchange as well
+            all_rows2 = [None] * world
+            dist.all_gather_object(all_rows2, rows)
+            pos = [0] * world
+            meta_rows = []
+            for n, r in zip(shards.sizes, shards.owner):
+                meta_rows.extend(all_rows2[r][pos[r]:pos[r] + n])
+                pos[r] += n
+    return x, y, meta_rows
+
+
+def _to_py(v):
+    if isinstance(v, torch.Tensor):
+        return v.item() if v.numel() == 1 else v.detach().cpu().tolist()
+    if isinstance(v, np.generic):
+        return v.item()
+    return v
+
+
+def metadata_rows(metadata, batch_size: int):
+    """Per-sample dicts from a collated metadata dict; defaults (with the reference's warnings) when it is missing
+    (aihab_utils/feature_cache.py:84-95)."""
+    if not isinstance(metadata, dict):
+        print("[warn] metadata missing; writing default values in metadata.csv." if metadata is None
+              else "[warn] metadata is not a dict; writing default values in metadata.csv.")
+        return [{} for _ in range(batch_size)]
+    cols = {k: (v.detach().cpu().tolist() if isinstance(v, torch.Tensor) and v.dim() > 0 else v)
+            for k, v in metadata.items()}   # one host conversion per column, not one .item() per sample
+    out = []
+    for i in range(batch_size):
+        out.append({k: _to_py(v[i]) if isinstance(v, (list, tuple, np.ndarray)) else _to_py(v) for k, v in cols.items()})
+    return out

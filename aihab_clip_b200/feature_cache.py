@@ -6,10 +6,17 @@ Same function names, arguments, return values, directory layout and file formats
 * ``<cache_embeddings_dir>/<backbone>_<dataset>/<split>/seed<seed>/{embeddings.pt, labels.pt, metadata.csv,
   meta.json}``                                                                            (ref :53-65, :147-174)
 
-What changes is where the work happens: batches go through the sm_100a engine (``model.encode_image`` for the
-preprocessed float batches a reference DataLoader yields, ``model.encode_image_u8`` for raw uint8 HWC batches),
-results stay in HBM for the whole pass and are copied to the host ONCE instead of per batch (the reference syncs
-on ``.to('cpu')`` every batch, methods/utils.py:164), and the L2 normalisation runs in the scoring kernel.
+plus the two remaining extraction loops of the reference, ``pre_load_features`` (utils.py:60-82, ``<split>_f.pt`` /
+``<split>_l.pt``) and ``build_cache_model`` (methods/utils.py:31-45).
+
+What changes is where the work happens.  Every function here is a thin caller of
+``extraction.extract_loader``: batches go through the sm_100a engine (``model.encode_image`` for the preprocessed
+float batches a reference DataLoader yields, ``model.encode_image_u8`` for raw uint8 HWC batches); the loader's batches
+are sharded BY IMAGE BATCH across the ranks of an initialised ``torch.distributed`` group (1/2/4/8 B200s, one process
+per GPU; a single process is the 1-GPU case); rows stay in HBM for the whole pass (the reference syncs on
+``.to('cpu')`` every batch, methods/utils.py:164), meet in ONE all-gather, and reach the host in ONE copy;
+normalisation runs in ``aihab_l2_normalize`` / the scoring kernel.  Rank 0 writes the files; every rank returns the
+same tensors.
 """
 from __future__ import annotations
 
@@ -22,6 +29,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .extraction import extract_loader, metadata_rows as _metadata_rows  # noqa: F401
 
 
 def _canonical_backbone_name(backbone: str) -> str:
@@ -77,141 +85,172 @@ def _model_device(clip_model) -> torch.device:
         return torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
 
 
-def _encode_batch(clip_model, images: torch.Tensor, device) -> torch.Tensor:
-    images = images.to(device, non_blocking=True)
-    if images.dtype == torch.uint8:  # raw HWC batch: GPU preprocessing fused in front of the tower
-        return clip_model.encode_image_u8(images)
-    return clip_model.encode_image(images)
+def _is_writer() -> bool:
+    import torch.distributed as dist
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
 
 
-def compute_image_features(clip_model, loader, to_cpu: bool = False):
+def _sync_ranks():
+    """Files written by rank 0 are visible to every rank when a writer returns."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
+def compute_image_features(clip_model, loader, to_cpu: bool = False, _encode_fn=None):
     """ref methods/utils.py:142-173 — pre-projection features ``[N, width]`` (model dtype) and labels for a loader
-    of ``(images, target)`` batches.  ``to_cpu=True`` returns CPU tensors (one device->host copy at the end)."""
-    device = _model_device(clip_model)
-    feats, labels = [], []
-    with torch.no_grad():
-        for images, target in loader:
-            feats.append(_encode_batch(clip_model, images, device))
-            labels.append(target.detach() if to_cpu else target.to(device, non_blocking=True))
-    x = torch.cat(feats, dim=0)
-    y = torch.cat(labels, dim=0)
-    if to_cpu:
-        x, y = x.detach().to("cpu"), y.to("cpu")
+    of ``(images, target)`` batches, in loader order.  ``to_cpu=True`` returns CPU tensors (ONE device->host copy at the
+    end; very large passes spill to pinned memory in bounded blocks, ``AIHAB_CACHE_SPILL_MB``)."""
+    x, y, _ = extract_loader(clip_model, loader, to_cpu=to_cpu, encode_fn=_encode_fn)
     return x, y
 
 
-def cache_preprojection_features(cfg, clip_bundle: dict, dl_tr, info: dict):
+def cache_preprojection_features(cfg, clip_bundle: dict, dl_tr, info: dict, _encode_fn=None):
     """ref :189-250 — writes f{v}.pth (features in model dtype) per augmentation view and label.pth (int64) once,
     then reloads each file to validate its shape."""
     clip_model = clip_bundle["clip_model"]
     cache_dir = _feature_cache_dir(cfg)
     num_views = int(cfg.get("aug_views", 1) or 1)
     expected_n = int(info.get("train_size", len(dl_tr.dataset)))
-    print("\n==== Feature Caching (pre-projection) ====")
-    print({"cache_dir": str(cache_dir), "backbone": cfg.get("backbone", "RN50"), "dataset": cfg.get("dataset", "cs"),
-           "shots": int(cfg.get("shots", 0) or 0), "seed": int(cfg.get("seed", 1) or 1), "aug_views": num_views,
-           "expected_train_size": expected_n})
-    clip_model.eval()
-    cache_dir.mkdir(parents=True, exist_ok=True)
+    writer = _is_writer()
+    if writer:
+        print("\n==== Feature Caching (pre-projection) ====")
+        print({"cache_dir": str(cache_dir), "backbone": cfg.get("backbone", "RN50"), "dataset": cfg.get("dataset", "cs"),
+               "shots": int(cfg.get("shots", 0) or 0), "seed": int(cfg.get("seed", 1) or 1), "aug_views": num_views,
+               "expected_train_size": expected_n})
+    if hasattr(clip_model, "eval"):
+        clip_model.eval()
     for v in range(num_views):
-        feats_t, labels_t = compute_image_features(clip_model, dl_tr, to_cpu=True)
-        fpath = cache_dir / f"f{v}.pth"
-        torch.save(feats_t, fpath)
-        print(f"[cache] view {v} -> {fpath}")
-        print({"features.shape": tuple(feats_t.shape), "features.dtype": str(feats_t.dtype)})
-        if v == 0:
-            lpath = cache_dir / "label.pth"
-            torch.save(labels_t, lpath)
-            print(f"[cache] labels -> {lpath}")
-            print({"labels.shape": tuple(labels_t.shape), "labels.dtype": str(labels_t.dtype),
-                   "num_unique_labels": int(labels_t.unique().numel())})
-        loaded = torch.load(fpath, map_location="cpu", weights_only=True)
-        print({"reload_shape_ok": tuple(loaded.shape) == tuple(feats_t.shape),
-               "rows_match_labels": feats_t.shape[0] == labels_t.shape[0],
-               "rows_match_expected": feats_t.shape[0] == expected_n})
-    print("\nFeature caching complete.")
-
-
-def _to_py(v: Any) -> Any:
-    if isinstance(v, torch.Tensor):
-        return v.item() if v.numel() == 1 else v.detach().cpu().tolist()
-    if isinstance(v, np.generic):
-        return v.item()
-    return v
-
-
-def _metadata_rows(metadata: Any, batch_size: int) -> List[Dict[str, Any]]:
-    """ref :84-95 — per-sample dicts from a collated metadata dict; defaults when missing."""
-    if not isinstance(metadata, dict):
-        print("[warn] metadata missing; writing default values in metadata.csv." if metadata is None
-              else "[warn] metadata is not a dict; writing default values in metadata.csv.")
-        return [{} for _ in range(batch_size)]
-    rows = []
-    for i in range(batch_size):
-        rows.append({k: _to_py(v[i] if isinstance(v, (list, tuple, np.ndarray, torch.Tensor)) else v)
-                     for k, v in metadata.items()})
-    return rows
+        feats_t, labels_t = compute_image_features(clip_model, dl_tr, to_cpu=True, _encode_fn=_encode_fn)
+        if writer:
+            fpath = cache_dir / f"f{v}.pth"
+            fpath.parent.mkdir(parents=True, exist_ok=True)
+            torch.save(feats_t, fpath)
+            print(f"[cache] view {v} -> {fpath}")
+            print({"features.shape": tuple(feats_t.shape), "features.dtype": str(feats_t.dtype)})
+            if v == 0:
+                lpath = cache_dir / "label.pth"
+                torch.save(labels_t, lpath)
+                print(f"[cache] labels -> {lpath}")
+                print({"labels.shape": tuple(labels_t.shape), "labels.dtype": str(labels_t.dtype),
+                       "num_unique_labels": int(labels_t.unique().numel())})
+            loaded = torch.load(fpath, map_location="cpu", weights_only=True)
+            print({"reload_shape_ok": tuple(loaded.shape) == tuple(feats_t.shape),
+                   "rows_match_labels": feats_t.shape[0] == labels_t.shape[0],
+                   "rows_match_expected": feats_t.shape[0] == expected_n})
+        _sync_ranks()
+    if writer:
+        print("\nFeature caching complete.")
 
 
 def cache_openclip_embeddings(cfg: dict, model: torch.nn.Module, loader, split: str = "test",
-                              checkpoint_path: Optional[str] = None) -> Path:
-    """ref :98-186 — embeddings.pt (optionally L2-normalised), labels.pt, metadata.csv, meta.json."""
+                              checkpoint_path: Optional[str] = None, _encode_fn=None, _normalize_fn=None) -> Path:
+    """ref :98-186 — embeddings.pt (optionally L2-normalised, model dtype), labels.pt (int64), metadata.csv,
+    meta.json."""
     import pandas as pd
     normalize = bool(cfg.get("finetune", {}).get("cache_embeddings_normalize", True))
     cache_dir = _embedding_cache_dir(cfg, split)
-    cache_dir.mkdir(parents=True, exist_ok=True)
-    device = _model_device(model)
-    model.eval()
-    feats_list, labels_list, rows = [], [], []
-    with torch.no_grad():
-        for batch in loader:
-            if isinstance(batch, (list, tuple)) and len(batch) == 3:
-                images, targets, metadata = batch
-            elif isinstance(batch, (list, tuple)) and len(batch) == 2:
-                images, targets = batch
-                metadata = None
-            else:
-                raise ValueError("Expected batch to be (images, targets) or (images, targets, metadata).")
-            feats = _encode_batch(model, images, device)
-            if normalize:  # F.normalize(feats, dim=-1) in the scoring kernel, cast back to the model dtype
-                emb, _, _, _ = ops.score(feats, None, None, k=0)
-                feats = emb.to(feats.dtype)
-            feats_list.append(feats)
-            targets_cpu = targets.detach().to("cpu")
-            labels_list.append(targets_cpu)
-            for i, row in enumerate(_metadata_rows(metadata, int(targets_cpu.shape[0]))):
-                rows.append({"file_name": row.get("file_name", ""),
-                             "ground_truth_num_label": int(targets_cpu[i].item()),
-                             "ground_truth_word_label": row.get("plot_word_label", ""),
-                             "ground_truth_L2_num_label": row.get("l2_label", -1)})
-    feats_all = torch.cat(feats_list, dim=0).detach().to("cpu")
-    labels_all = torch.cat(labels_list, dim=0)
-    torch.save(feats_all, cache_dir / "embeddings.pt")
-    torch.save(labels_all, cache_dir / "labels.pt")
-    columns = ["file_name", "ground_truth_num_label", "ground_truth_word_label", "ground_truth_L2_num_label"]
-    pd.DataFrame(rows).reindex(columns=columns).to_csv(cache_dir / "metadata.csv", index=False)
-    info = {"timestamp": datetime.now().strftime("%Y-%m-%d %H:%M:%S"), "split": str(split), "normalized": normalize,
-            "num_samples": int(feats_all.shape[0]), "dim": int(feats_all.shape[1]) if feats_all.ndim == 2 else None,
-            "checkpoint_path": str(checkpoint_path) if checkpoint_path is not None else None,
-            "cache_dir": str(cache_dir)}
-    (cache_dir / "meta.json").write_text(json.dumps(info, indent=2))
-    print("\n==== OpenCLIP Embedding Cache ====")
-    print({"cache_dir": str(cache_dir), "num_samples": info["num_samples"], "dim": info["dim"],
-           "normalized": normalize})
+    if hasattr(model, "eval"):
+        model.eval()
+    post = None
+    if normalize:  # F.normalize(feats, dim=-1), ref :126-127 — in the model dtype, fp32 statistics
+        post = _normalize_fn or (lambda f: ops.l2_normalize(f, 1e-12))
+    feats_all, labels_all, meta = extract_loader(model, loader, post_fn=post, to_cpu=True, want_metadata=True,
+                                                 encode_fn=_encode_fn)
+    if _is_writer():
+        cache_dir.mkdir(parents=True, exist_ok=True)
+        torch.save(feats_all, cache_dir / "embeddings.pt")
+        torch.save(labels_all, cache_dir / "labels.pt")
+        labels_py = labels_all.tolist()   # one conversion, no per-sample .item()
+        rows = [{"file_name": row.get("file_name", ""), "ground_truth_num_label": int(lab),
+                 "ground_truth_word_label": row.get("plot_word_label", ""),
+                 "ground_truth_L2_num_label": row.get("l2_label", -1)} for row, lab in zip(meta, labels_py)]
+        columns = ["file_name", "ground_truth_num_label", "ground_truth_word_label", "ground_truth_L2_num_label"]
+        pd.DataFrame(rows).reindex(columns=columns).to_csv(cache_dir / "metadata.csv", index=False)
+        info = {"timestamp": datetime.now().strftime("%Y-%m-%d %H:%M:%S"), "split": str(split), "normalized": normalize,
+                "num_samples": int(feats_all.shape[0]), "dim": int(feats_all.shape[1]) if feats_all.ndim == 2 else None,
+                "checkpoint_path": str(checkpoint_path) if checkpoint_path is not None else None,
+                "cache_dir": str(cache_dir)}
+        (cache_dir / "meta.json").write_text(json.dumps(info, indent=2))
+        print("\n==== OpenCLIP Embedding Cache ====")
+        print({"cache_dir": str(cache_dir), "embeddings": str(cache_dir / "embeddings.pt"),
+               "labels": str(cache_dir / "labels.pt"), "metadata": str(cache_dir / "metadata.csv"),
+               "num_samples": info["num_samples"], "dim": info["dim"], "normalized": normalize})
+    _sync_ranks()
     return cache_dir
 
 
-def compute_image_features_test(clip_model, loader, proj, text_weights) -> float:
-    """ref methods/utils.py:175-189 — zero-shot accuracy (%): encode -> proj -> normalise -> 100 * f @ W -> argmax.
-    ``proj`` is a ``[width, embed]`` tensor or a module with a ``vit_proj`` parameter (methods/ProLIP.py:31-41)."""
-    device = _model_device(clip_model)
+def _project_fn(proj, device):
+    """x -> proj(x): a ``[width, embed]`` tensor, a module with a ``vit_proj`` parameter (VisProjViT,
+    methods/ProLIP.py:31-41), or any callable."""
     p = getattr(proj, "vit_proj", proj)
-    correct, total = 0, 0
-    with torch.no_grad():
-        for images, target in loader:
-            feats = _encode_batch(clip_model, images, device)
-            _, _, idx, _ = ops.score(feats, p.to(device), text_weights.to(device), 100.0, 1, want_emb=False,
-                                     want_logits=False)
-            correct += int((idx[:, 0].cpu() == target.cpu()).sum())
-            total += int(target.shape[0])
-    return 100.0 * correct / max(total, 1)
+    if torch.is_tensor(p):
+        return p.detach().to(device), None
+    return None, proj
+
+
+def compute_image_features_test(clip_model, loader, proj, text_weights) -> float:
+    """ref methods/utils.py:175-189 — zero-shot accuracy (%): encode -> proj -> normalise -> 100 * f @ W -> argmax."""
+    device = _model_device(clip_model)
+    p, call = _project_fn(proj, device)
+    tw = text_weights.detach().to(device)
+
+    def post(f):
+        if call is not None:   # a generic projector module: its forward, then normalise + logits + argmax in the kernel
+            _, _, idx, _ = ops.score(call(f), None, tw, 100.0, 1, want_emb=False, want_logits=False)
+        else:
+            _, _, idx, _ = ops.score(f, p, tw, 100.0, 1, want_emb=False, want_logits=False)
+        return idx.to(torch.float32)   # [n, 1]; exact for C < 2**24, rides in the single all-gather
+
+    preds, labels, _ = extract_loader(clip_model, loader, post_fn=post, to_cpu=True)
+    if preds.shape[0] == 0:
+        return 0.0
+    return 100.0 * float((preds[:, 0].to(torch.int64) == labels).double().mean())
+
+
+def pre_load_features(cfg, split, clip_model, loader):
+    """ref utils.py:60-82 — ``encode_image`` -> ``f /= f.norm(dim=-1, keepdim=True)`` (NO eps: a zero row becomes NaN
+    as in the reference) -> ``<cache_dir>/<split>_f.pt`` / ``<split>_l.pt``; loads them when ``cfg['load_pre_feat']``.
+    Returns (features, labels) on the model's device like the reference."""
+    if cfg["load_pre_feat"] is False:
+        features, labels, _ = extract_loader(clip_model, loader, post_fn=lambda f: ops.l2_normalize(f, 0.0))
+        if _is_writer():
+            torch.save(features, cfg["cache_dir"] + "/" + split + "_f.pt")
+            torch.save(labels, cfg["cache_dir"] + "/" + split + "_l.pt")
+        _sync_ranks()
+    else:
+        features = torch.load(cfg["cache_dir"] + "/" + split + "_f.pt")
+        labels = torch.load(cfg["cache_dir"] + "/" + split + "_l.pt")
+    return features, labels
+
+
+def build_cache_model(cfg, clip_model, train_loader_cache, task, proj):
+    """ref methods/utils.py:31-45 — Tip-Adapter style cache: per augment epoch encode -> proj -> F.normalize, mean over
+    the epochs, renormalise (no eps), transpose to ``[embed, N]``; values = one-hot labels in fp16.  (The reference's
+    ``load_cache`` branch is broken — it passes undefined tensors to torch.load, methods/utils.py:57-60 — so only the
+    build branch exists here.)"""
+    if cfg["load_cache"] is not False:
+        raise NotImplementedError("build_cache_model(load_cache=True) is a dead path in the reference "
+                                  "(methods/utils.py:57-60 calls torch.load on undefined tensors)")
+    device = _model_device(clip_model)
+    p, call = _project_fn(proj, device)
+
+    def post(f):   # proj(x) -> F.normalize(dim=-1), ref :38-39; fp32 embedding from the scoring kernel, model dtype out
+        if call is not None:
+            return ops.l2_normalize(call(f), 1e-12)
+        emb, _, _, _ = ops.score(f, p, None, k=0)
+        return emb.to(f.dtype)
+
+    keys, values = [], None
+    for augment_idx in range(cfg["augment_epoch"]):
+        print("Augment Epoch: {:} / {:}".format(augment_idx, cfg["augment_epoch"]))
+        feats, labels, _ = extract_loader(clip_model, train_loader_cache, post_fn=post)
+        keys.append(feats.unsqueeze(0))
+        if augment_idx == 0:
+            values = labels
+    cache_keys = torch.cat(keys, dim=0).mean(dim=0)
+    cache_keys = ops.l2_normalize(cache_keys, 0.0)           # cache_keys /= cache_keys.norm(dim=-1, keepdim=True)
+    cache_keys = cache_keys.permute(1, 0)
+    cache_values = torch.nn.functional.one_hot(values).half()
+    Path(cfg["cache_dir"]).mkdir(parents=True, exist_ok=True)
+    return cache_keys, cache_values

@@ -107,6 +107,21 @@ def score(feats: torch.Tensor, proj, text_w, scale: float = 100.0, k: int = 1, w
     return emb, logits, idx, val
 
 
+def l2_normalize(x: torch.Tensor, eps: float = 1e-12, out_dtype: torch.dtype | None = None) -> torch.Tensor:
+    """Rows of x [n, D] (fp32 / fp16 / bf16) divided by max(||row||_2, eps), fp32 statistics, one 128-bit-load kernel.
+    eps = 1e-12 is F.normalize (aihab_utils/feature_cache.py:126-127); eps = 0 is `f /= f.norm(dim=-1, keepdim=True)`
+    (utils.py:69)."""
+    _need_cuda(x)
+    if x.dim() != 2:
+        raise ValueError("l2_normalize expects a 2-D tensor [rows, cols]")
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    rc = _lib.load().aihab_l2_normalize(_ptr(x), dtype_code(x.dtype), x.shape[0], x.shape[1], C.c_float(eps), _ptr(out),
+                                        dtype_code(out.dtype), _stream(x.device))
+    _lib.check(rc, "aihab_l2_normalize")
+    return out
+
+
 def score16(feats16: torch.Tensor, proj16: torch.Tensor, text_w: torch.Tensor, scale: float = 100.0, k: int = 1,
             want_emb: bool = False, want_logits: bool = False):
     """Tensor-core scoring over cached 16-bit features (config 5: ProLIP / linear-probe scoring).  feats16 [n, D]

@@ -237,3 +237,41 @@ def test_text_tower_on_tensor_cores_matches_reference_golden(tmp_path, cuda_devi
     assert torch.equal(xb, xb2)
     with pytest.raises(RuntimeError):
         model.encode_text(tok.cpu())
+
+
+@pytest.mark.parametrize("case", ["outlier_channels", "common_offset", "both"])
+def test_layernorm_fold_with_outlier_activations(tmp_path, cuda_device, monkeypatch, capsys, case):
+    """the LayerNorm fold (un-normalised gamma*x as the 16-bit GEMM operand, statistics from per-block
+    partials) was only validated on random-init weights without activation outliers.  Here the residual stream carries
+    what pretrained CLIP towers carry — a few channels ~300x larger than the rest and / or a large common per-row
+    offset (injected through ln_pre's affine, so every later LayerNorm sees them) — and the folded path must stay
+    finite, agree with the unfused path (AIHAB_LNFOLD=0) and with the fp32 numpy oracle."""
+    import aihab_clip_b200.clip as clip
+    geom = GEOMETRIES["ViT-tiny/14"]
+    sd = make_state_dict_np(geom, 1, with_text=True)
+    if case in ("outlier_channels", "both"):
+        for c in (3, 77, 200):
+            sd["visual.ln_pre.weight"][c] = 300.0
+    if case in ("common_offset", "both"):
+        sd["visual.ln_pre.bias"] = sd["visual.ln_pre.bias"] + 25.0
+    path = tmp_path / "outlier.pt"
+    torch.save({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, path)
+    u8 = synthetic_images_u8(6, 56, smooth=True)
+    x_np = np.stack([O.clip_preprocess(im, geom.image_resolution) for im in u8])
+    ref = O.encode_image({k: v for k, v in sd.items() if k.startswith("visual.")}, x_np)
+    out = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("AIHAB_LNFOLD", fold)
+        _, model, _ = clip.load(str(path), device=cuda_device)
+        model.float()
+        out[fold] = model.encode_image(torch.from_numpy(x_np).to(cuda_device)).cpu().numpy()
+        del model
+    err_fold = float(np.abs(out["1"] - ref).max())
+    err_plain = float(np.abs(out["0"] - ref).max())
+    with capsys.disabled():
+        print(f"\n[ln-fold outliers: {case}] max |dfeat| folded {err_fold:.2e}  unfused {err_plain:.2e}  "
+              f"folded vs unfused {np.abs(out['1'] - out['0']).max():.2e}")
+    assert np.isfinite(out["1"]).all() and np.isfinite(out["0"]).all()
+    assert cosine(out["1"], ref).min() >= 0.999 and cosine(out["0"], ref).min() >= 0.999
+    assert err_plain <= 1e-2
+    assert err_fold <= 1e-2

@@ -191,12 +191,15 @@ def test_preferred_batch_fills_whole_waves():
 
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exits 0 without a GPU, prints exactly one
-    JSON line with the base contract's keys plus impl / cpu_baseline / e2e, and times the torch-operator restatement."""
+    JSON line with the base contract's keys plus impl / cpu_baseline / e2e, and times the UNMODIFIED reference from
+    oracle/_ref when that archive is built (else the torch-operator port)."""
     import json
     import subprocess
     import sys
     from pathlib import Path
     repo = Path(__file__).resolve().parent.parent
+    from oracle import build_ref
+    build_ref.build(verbose=False)   # no-op where /root/reference is absent
     out = subprocess.run([sys.executable, str(repo / "bench.py"), "--impl", "reference", "--arch", "ViT-tiny/16",
                           "--steps", "2", "--warmup", "1", "--ref-batch", "4"], capture_output=True, text=True,
                          timeout=300, cwd=repo)
@@ -208,12 +211,36 @@ def test_bench_reference_arm_prints_the_contract_line():
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["value"] > 0 and d["steps"] == 2
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
-    assert "clip_oracle_torch" in d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["cores"] >= 1
+    if build_ref.available():
+        assert d["cpu_baseline"]["kind"] == "reference" and "oracle/_ref" in d["cpu_baseline"]["sample"]
+    else:
+        assert d["cpu_baseline"]["kind"] == "port" and "clip_oracle_torch" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # both arms describe the workload with the same `config` object (the driver's same_config check)
+    import argparse
+    import bench
+    from aihab_clip_b200.weights import GEOMETRIES
+    a = argparse.Namespace(arch="ViT-tiny/16", classes=20, batch=256)
+    assert d["config"] == bench.make_config(a, GEOMETRIES["ViT-tiny/16"], 1)
     # rank != 0 of a torchrun launch exits 0 without work and without output
     import os
     env = dict(os.environ, RANK="1")
     quiet = subprocess.run([sys.executable, str(repo / "bench.py"), "--impl", "reference", "--arch", "ViT-tiny/16"],
                            capture_output=True, text=True, timeout=300, cwd=repo, env=env)
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+def test_reference_archive_is_the_unmodified_reference():
+    """oracle/_ref/reference_path.zip (built here from /root/reference, git-ignored) holds byte-identical copies."""
+    import zipfile
+    from pathlib import Path
+    from oracle import build_ref
+    if not build_ref.REF_SRC.is_dir():
+        pytest.skip("/root/reference is not present on this box")
+    build_ref.build(verbose=False)
+    with zipfile.ZipFile(build_ref.ARCHIVE) as z:
+        for rel in build_ref.FILES:
+            assert z.read(rel) == (build_ref.REF_SRC / rel).read_bytes(), rel
+    ignored = (Path(__file__).resolve().parent.parent / ".gitignore").read_text()
+    assert "oracle/_ref/" in ignored
