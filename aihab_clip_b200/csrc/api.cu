@@ -33,7 +33,7 @@ struct ProfRec {
   int aux;  // site tag within a class (GEMM: N)
 };
 std::mutex g_prof_mu;
-bool g_prof_on = false;
+std::atomic<bool> g_prof_on{false};
 std::vector<ProfRec> g_prof_recs;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
 
@@ -88,24 +88,36 @@ int fail(const std::string& msg) {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// Stream-ordered temporary that is returned to the pool on EVERY exit path (the CK macros return early on errors).
+template <typename T>
+struct AsyncTemp {
+  T* p = nullptr;
+  cudaStream_t s;
+  explicit AsyncTemp(cudaStream_t stream) : s(stream) {}
+  AsyncTemp(const AsyncTemp&) = delete;
+  AsyncTemp& operator=(const AsyncTemp&) = delete;
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, s); }
+  ~AsyncTemp() {
+    if (p != nullptr) cudaFreeAsync(p, s);
+  }
+};
+
 // attention kernel choice: 3 = persistent flash tcgen05 (L > 224), 2 = persistent tcgen05 (64 < L <= 224; with
-// AIHAB_ATTN_PACK=1 also 16 <= L <= 64, images packed block-diagonally),
-// 1 = tcgen05 (L <= 256), 0 = mma.sync (any L <= 908).
-// AIHAB_ATTN=legacy|tc|tcp caps the choice (A/B measurements); default picks the fastest supported kernel.
+// AIHAB_ATTN_PACK=1 also 16 <= L <= 64, images packed block-diagonally), 0 = mma.sync (any L <= 908).
+// AIHAB_ATTN=legacy|tcp caps the choice (A/B measurements); default picks the fastest supported kernel.
 int attention_kind(int L) {
   int cap = 3;
   if (const char* e = getenv("AIHAB_ATTN")) {
     if (!strcmp(e, "legacy")) cap = 0;
-    else if (!strcmp(e, "tc")) cap = 1;
     else if (!strcmp(e, "tcp")) cap = 2;
   }
   if (cap >= 2 && aihab::attention_tcp_supported(L)) return 2;
   if (cap >= 3 && aihab::attention_tcf_supported(L)) return 3;
-  if (cap >= 1 && aihab::attention_tc_supported(L)) return 1;
   return 0;
 }
 int attention_key_box(int kind, int L) {
-  return kind == 3 ? 32 : (kind == 2 ? aihab::attention_tcp_key_rows(L) : aihab::attention_tc_key_rows(L));
+  (void)kind;
+  return kind == 3 ? 32 : aihab::attention_tcp_key_rows(L);
 }
 
 struct DeviceGuard {
@@ -226,8 +238,11 @@ struct DeviceTables {
   int* v_bounds = nullptr;
   int* v_coeffs = nullptr;
   aihab::ResampleTables t{};
+  uint64_t last_use = 0;
 };
 
+constexpr size_t kMaxTableSets = 32;  // distinct (device, input size, R) combinations kept; least recently used evicted
+uint64_t g_tab_clock = 0;
 std::mutex g_tab_mu;
 std::map<std::tuple<int, int, int, int>, DeviceTables> g_tables;  // (device, sh, sw, R)
 
@@ -271,8 +286,20 @@ int get_tables(int dev, int sh, int sw, int R, aihab::ResampleTables* out) {
     d.t.crop_left = static_cast<int>(std::nearbyint((new_w - R) / 2.0));
     d.t.need_h = (new_w != sw);
     d.t.need_v = (new_h != sh);
+    if (g_tables.size() >= kMaxTableSets) {  // variable-size image sets must not grow device memory without bound
+      auto victim = g_tables.begin();
+      for (auto j = g_tables.begin(); j != g_tables.end(); ++j)
+        if (j->second.last_use < victim->second.last_use) victim = j;
+      // cudaFree synchronises the device, so no kernel still reads the evicted tables
+      cudaFree(victim->second.h_bounds);
+      cudaFree(victim->second.h_coeffs);
+      cudaFree(victim->second.v_bounds);
+      cudaFree(victim->second.v_coeffs);
+      g_tables.erase(victim);
+    }
     it = g_tables.emplace(key, d).first;
   }
+  it->second.last_use = ++g_tab_clock;
   *out = it->second.t;
   return 0;
 }
@@ -488,8 +515,6 @@ int run_blocks(aihab_vit* h, int n, cudaStream_t s) {
       else if (h->attn_kind == 2)
         CKL(aihab::launch_attention_tcp(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, h->num_sms, s,
                                         next_dir(), h->causal));
-      else if (h->attn_kind == 1)
-        CKL(aihab::launch_attention_tc(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, s));
       else
         CKL(aihab::launch_attention(h->big, h->y, n, L, h->cfg.heads, h->bf16, s));
     }
@@ -758,7 +783,10 @@ int aihab_vit_create(const aihab_vit_config* cfg, const aihab_vit_weights* w, in
     if (upload_f32(h, cls.data(), D, &h->cls0)) return bail(1);
   }
   if (build_stack(h, cfg->layers, w->blocks, static_cast<size_t>(cfg->max_batch) * h->g2)) return bail(1);
-  CK(cudaDeviceSynchronize());
+  if (cudaError_t e = cudaDeviceSynchronize(); e != cudaSuccess) {
+    fail(std::string("aihab_vit_create: ") + cudaGetErrorString(e));
+    return bail(1);
+  }
   *out = h;
   return 0;
 }
@@ -828,7 +856,10 @@ int aihab_text_create(const aihab_text_config* cfg, const aihab_text_weights* w,
     fail("aihab_text_create: the causal mask needs the persistent tcgen05 attention (AIHAB_ATTN must not cap it)");
     return bail(1);
   }
-  CK(cudaDeviceSynchronize());
+  if (cudaError_t e = cudaDeviceSynchronize(); e != cudaSuccess) {
+    fail(std::string("aihab_text_create: ") + cudaGetErrorString(e));
+    return bail(1);
+  }
   *out = reinterpret_cast<aihab_text*>(h);
   return 0;
 }
@@ -976,10 +1007,11 @@ int aihab_score(const float* feats, int n, int D, const float* proj, int E, cons
   // rows per pass bounded so temporaries stay small (config 5: 1M rows x 1000 classes)
   keep_pool_warm(dev);
   const int chunk = 65536;
-  float *emb_tmp = nullptr, *logit_tmp = nullptr;
+  AsyncTemp<float> emb_t(s), logit_t(s);
   const int rows_tmp = std::min(n, chunk);
-  if (emb_out == nullptr) CK(cudaMallocAsync(&emb_tmp, static_cast<size_t>(rows_tmp) * E * 4, s));
-  if (text_w != nullptr && logits_out == nullptr) CK(cudaMallocAsync(&logit_tmp, static_cast<size_t>(rows_tmp) * C * 4, s));
+  if (emb_out == nullptr) CK(emb_t.alloc(static_cast<size_t>(rows_tmp) * E * 4));
+  if (text_w != nullptr && logits_out == nullptr) CK(logit_t.alloc(static_cast<size_t>(rows_tmp) * C * 4));
+  float *emb_tmp = emb_t.p, *logit_tmp = logit_t.p;
   ProfScope ps(PC_SCORE, 2.0 * n * (static_cast<double>(proj ? D : 0) * E + static_cast<double>(text_w ? E : 0) * C), s);
   for (int i0 = 0; i0 < n; i0 += chunk) {
     const int nb = std::min(chunk, n - i0);
@@ -999,8 +1031,6 @@ int aihab_score(const float* feats, int n, int D, const float* proj, int E, cons
                                topk_val ? topk_val + static_cast<size_t>(i0) * k : nullptr, s));
     }
   }
-  if (emb_tmp) CK(cudaFreeAsync(emb_tmp, s));
-  if (logit_tmp) CK(cudaFreeAsync(logit_tmp, s));
   return 0;
 }
 
@@ -1035,13 +1065,15 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
   const int sms = sm_count(dev);
   const int chunk = 32768;
   const int rows_tmp = std::min(n, chunk);
-  void *projT = nullptr, *w3 = nullptr, *a3 = nullptr;
-  float *emb_raw = nullptr, *logit_tmp = nullptr;
-  CK(cudaMallocAsync(&projT, static_cast<size_t>(E) * D * 2, s));
-  CK(cudaMallocAsync(&w3, static_cast<size_t>(C) * 3 * E * 2, s));
-  CK(cudaMallocAsync(&a3, static_cast<size_t>(rows_tmp) * 3 * E * 2, s));
-  CK(cudaMallocAsync(&emb_raw, static_cast<size_t>(rows_tmp) * E * 4, s));
-  if (logits_out == nullptr) CK(cudaMallocAsync(&logit_tmp, static_cast<size_t>(rows_tmp) * C * 4, s));
+  AsyncTemp<uint8_t> projT_t(s), w3_t(s), a3_t(s);
+  AsyncTemp<float> emb_raw_t(s), logit_t(s);
+  CK(projT_t.alloc(static_cast<size_t>(E) * D * 2));
+  CK(w3_t.alloc(static_cast<size_t>(C) * 3 * E * 2));
+  CK(a3_t.alloc(static_cast<size_t>(rows_tmp) * 3 * E * 2));
+  CK(emb_raw_t.alloc(static_cast<size_t>(rows_tmp) * E * 4));
+  if (logits_out == nullptr) CK(logit_t.alloc(static_cast<size_t>(rows_tmp) * C * 4));
+  void *projT = projT_t.p, *w3 = w3_t.p, *a3 = a3_t.p;
+  float *emb_raw = emb_raw_t.p, *logit_tmp = logit_t.p;
   ProfScope ps(PC_SCORE, 2.0 * n * (static_cast<double>(D) * E + static_cast<double>(E) * C), s);
   CKL(aihab::launch_transpose16(proj16, projT, D, E, s));   // [D, E] -> [E, D]: K-major operand B
   CKL(aihab::launch_split_textw(text_w, E, C, w3, s));      // [E, C] fp32 -> [C, 3E] fp16 (hi | lo | hi)
@@ -1081,11 +1113,6 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
       CKL(aihab::launch_topk(lg, nb, C, k, topk_idx + static_cast<size_t>(i0) * k,
                              topk_val ? topk_val + static_cast<size_t>(i0) * k : nullptr, s));
   }
-  CK(cudaFreeAsync(projT, s));
-  CK(cudaFreeAsync(w3, s));
-  CK(cudaFreeAsync(a3, s));
-  CK(cudaFreeAsync(emb_raw, s));
-  if (logit_tmp) CK(cudaFreeAsync(logit_tmp, s));
   return 0;
 }
 
@@ -1102,18 +1129,22 @@ int aihab_prototype_scores(const float* emb, const int64_t* labels, int n, int E
   keep_pool_warm(dev);
   const int chunk = 65536;  // rows per pass: the [rows, P] similarity tile stays small
   const int rows_tmp = std::min(n, chunk);
-  float* sim = nullptr;
-  CK(cudaMallocAsync(&sim, static_cast<size_t>(rows_tmp) * P * 4, s));
+  AsyncTemp<float> sim_t(s);
+  CK(sim_t.alloc(static_cast<size_t>(rows_tmp) * P * 4));
+  float* sim = sim_t.p;
   ProfScope ps(PC_SCORE, 2.0 * n * static_cast<double>(E) * P, s);
   const bool tensor = (E % 8) == 0 && (P % 4) == 0;
+  AsyncTemp<uint8_t> a3_t(s), w3_t(s);
   void *a3 = nullptr, *w3 = nullptr;
   const int sms = sm_count(dev);
   if (tensor) {
     // sim = e_hi p_hi + e_hi p_lo + e_lo p_hi as ONE K = 3E fp16 tcgen05 GEMM with fp32 accumulation (relative error
     // ~2^-21, the hi/lo split of aihab_score16) instead of an fp32 CUDA-core GEMM
     CK(aihab::gemm_init());
-    CK(cudaMallocAsync(&a3, static_cast<size_t>(rows_tmp) * 3 * E * 2, s));
-    CK(cudaMallocAsync(&w3, static_cast<size_t>(P) * 3 * E * 2, s));
+    CK(a3_t.alloc(static_cast<size_t>(rows_tmp) * 3 * E * 2));
+    CK(w3_t.alloc(static_cast<size_t>(P) * 3 * E * 2));
+    a3 = a3_t.p;
+    w3 = w3_t.p;
     CKL(aihab::launch_split_textw(prototypes_t, E, P, w3, s));  // [E, P] fp32 -> [P, 3E] fp16 (hi | lo | hi)
   }
   for (int i0 = 0; i0 < n; i0 += chunk) {
@@ -1142,9 +1173,6 @@ int aihab_prototype_scores(const float* emb, const int64_t* labels, int n, int E
                                        prototype_id ? prototype_id + i0 : nullptr, sim_to_other ? sim_to_other + i0 : nullptr,
                                        margin ? margin + i0 : nullptr, s));
   }
-  CK(cudaFreeAsync(sim, s));
-  if (a3) CK(cudaFreeAsync(a3, s));
-  if (w3) CK(cudaFreeAsync(w3, s));
   return 0;
 }
 
@@ -1243,10 +1271,8 @@ int aihab_attention(const void* qkv, void* out, int n, int L, int H, int dtype, 
     CK(aihab::make_tmap_2d_16bit(&mkv, qkv, rows, 3 * H * 64, pitch, attention_key_box(kind, L), bf16));
     if (kind == 3)
       CKL(aihab::launch_attention_tcf(mq, mkv, qkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream)));
-    else if (kind == 2)
-      CKL(aihab::launch_attention_tcp(mq, mkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream)));
     else
-      CKL(aihab::launch_attention_tc(mq, mkv, out, n, L, H, bf16, static_cast<cudaStream_t>(stream)));
+      CKL(aihab::launch_attention_tcp(mq, mkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream)));
     return 0;
   }
   CKL(aihab::launch_attention(qkv, out, n, L, H, dtype == AIHAB_BF16, static_cast<cudaStream_t>(stream)));

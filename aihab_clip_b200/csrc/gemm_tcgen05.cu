@@ -14,21 +14,11 @@ constexpr int BK = 64;       // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;   // fixed for 16-bit operands
 constexpr int EPI_WARP0 = 4;  // warps 4.. are the epilogue (warp % 4 selects the TMEM lane quadrant)
 // Two warps per TMEM lane quadrant (8 epilogue warps, 384 threads) so the epilogue keeps up with the MMA.  The fp32
-// residual epilogue streams 4 KB TMA boxes through per-warp rings, one warp per quadrant.  -DAIHAB_RES_WARPS_PAIR=8
-// runs it on two warps per quadrant in CTA pairs (each owns one 128-column half of the tile; operand stages / ring
-// slots via AIHAB_RES_STAGES_PAIR / AIHAB_RES_RS_PAIR): measured on B200 it is no faster (out_proj 0.0747 -> 0.0759 ms
-// hot, step unchanged) - in the step these GEMMs wait for DRAM, not for the epilogue warps - so the default stays 4.
-#ifndef AIHAB_RES_WARPS_PAIR
-#define AIHAB_RES_WARPS_PAIR 4
-#endif
-#ifndef AIHAB_RES_STAGES_PAIR
-#define AIHAB_RES_STAGES_PAIR 4
-#endif
-#ifndef AIHAB_RES_RS_PAIR
-#define AIHAB_RES_RS_PAIR 2
-#endif
+// residual epilogue streams 4 KB TMA boxes through per-warp rings, one warp per quadrant (two per quadrant were
+// measured no faster in round 1: in the step these GEMMs wait for DRAM, not for the epilogue warps).
 __host__ __device__ constexpr int epi_warps(int epi, bool two) {
-  return epi == EPI_BIAS_RES_32 ? (two ? AIHAB_RES_WARPS_PAIR : 4) : 8;
+  (void)two;
+  return epi == EPI_BIAS_RES_32 ? 4 : 8;
 }
 __host__ __device__ constexpr int num_threads(int epi, bool two) { return (EPI_WARP0 + epi_warps(epi, two)) * 32; }
 
@@ -44,9 +34,9 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int kResWarps = epi_warps(EPI_BIAS_RES_32, TWO);  // residual epilogue warps (rings)
-  static constexpr int kRS = (TWO && kResWarps == 8) ? AIHAB_RES_RS_PAIR : 4;  // ring slots per residual epilogue warp
+  static constexpr int kRS = 4;  // ring slots per residual epilogue warp
   static constexpr int kStages =
-      TWO ? (kRes ? (kResWarps == 8 ? AIHAB_RES_STAGES_PAIR : 4) : 5) : ((BN == 256) ? 3 : (kRes ? 4 : 5));
+      TWO ? (kRes ? 4 : 5) : ((BN == 256) ? 3 : (kRes ? 4 : 5));
   static constexpr int kStageBytes = kABytes + kBBytes;
   // residual rings (kResWarps x kRS boxes) + 2 KB per warp for the coalesced gamma*x store | 8 warps x 4 KB staging tile
   static constexpr int kStagingBytes = kRes ? kResWarps * (kRS * RES_BOX + 2048) : 8 * 4096;

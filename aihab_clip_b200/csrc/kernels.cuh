@@ -33,17 +33,10 @@ cudaError_t attention_init(int max_L);
 cudaError_t launch_attention_rows(const void* qkv, void* out, int n_img, int L, int H, int is_bf16, int q_row0,
                                   cudaStream_t stream);
 
-// tcgen05 / TMEM variant for 64 < L <= 256 (ViT-B/16's 197 tokens): S and O live in TMEM, softmax reads S with
-// tcgen05.ld.  tmap_q: make_tmap_2d_16bit over qkv [n*L, 3D] with a 128-row box; tmap_kv: same matrix with an
-// attention_tc_key_rows(L)-row box.
-bool attention_tc_supported(int L);
-int attention_tc_key_rows(int L);
-cudaError_t launch_attention_tc(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
-                                int H, int is_bf16, cudaStream_t stream);
-
 // Persistent, software-pipelined variant (64 < L <= 224; opt-in for 16 <= L <= 64, where several images share a tile
 // behind a block-diagonal mask): one CTA per SM, double-buffered Q/K/V stages and S buffers,
-// epilogue of item i-1 overlapped with the PV MMA.  Tensor maps as for launch_attention_tc, K / V box of
+// epilogue of item i-1 overlapped with the PV MMA.  tmap_q: make_tmap_2d_16bit over qkv [n*L, 3D] with a 128-row box;
+// tmap_kv: same matrix with a K / V box of
 // attention_tcp_key_rows(L) rows.
 bool attention_tcp_supported(int L);
 int attention_tcp_pack(int L);      // images per packed sequence (1 for L > 64)

@@ -2,6 +2,7 @@
 // alloc/ld, commit, fences), cp.async, ldmatrix and mma.sync.  Nothing here is portable below
 // sm_100a; the library is compiled with -gencode arch=compute_100a,code=sm_100a only.
 #pragma once
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -48,10 +49,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// -DAIHAB_DEBUG_HANG (make DEBUG_HANG=1, tools/sanitize.sh): every wait is bounded; a barrier that never completes (a
+// wrong phase, a descriptor / byte-count bug) prints who waited on what and traps instead of spinning until the
+// driver's watchdog kills the job.
+#ifdef AIHAB_DEBUG_HANG
+#ifndef AIHAB_DEBUG_HANG_SPINS
+#define AIHAB_DEBUG_HANG_SPINS (1u << 26)
+#endif
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_smem, uint32_t parity) {
+  printf("[aihab] mbarrier wait timed out: block %d thread %d barrier smem+0x%x parity %u\n", static_cast<int>(blockIdx.x),
+         static_cast<int>(threadIdx.x), bar_smem, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > AIHAB_DEBUG_HANG_SPINS) mbar_timeout(smem_u32(bar), parity);
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+#endif
 // Polling wait for single-thread roles (TMA producer / MMA issuer) that share an SM sub-partition with compute warps:
 // back off between polls so the spin loop does not eat their issue slots.
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {

@@ -28,16 +28,42 @@ def build_l3_to_l2_map():
     return [l2 for _, l2 in _L3], list(L2_NAMES)
 
 
-def gen_prompts(use_hierarchy: bool = True, use_descriptive: bool = False):
-    """data/templates.py:236-297 without the descriptive-attribute variants (their attribute dictionaries are
-    dataset prose, not part of the hot path): returns (prompts, templates_per_class)."""
-    if use_descriptive:
-        raise NotImplementedError("descriptive prompt attributes are not carried by the B200 hot-path package")
+def _descriptive():
+    """Per-class attribute phrases and the two descriptive templates of data/templates.py:12-201 (dataset prose kept as
+    a data file, exported from the reference by tools/export_prompt_data.py)."""
+    import json
+    from pathlib import Path
+    return json.loads((Path(__file__).resolve().parent / "descriptive_attrs.json").read_text())
+
+
+def gen_prompts(use_hierarchy: bool = True, use_descriptive: bool = True):
+    """data/templates.py:236-297 — prompts for the 20 L3 classes, class-major: with the L2 context
+    (``use_hierarchy``) or the flat CS_TEMPLATES, with the per-class descriptive attributes appended
+    (``use_descriptive``; prints a two-prompt preview per class like the reference).  Returns
+    ``(prompts, templates_per_class)``."""
+    base_templates = ["a habitat photo of {l2}, specifically {l3}"] if use_hierarchy else CS_TEMPLATES
+    desc = _descriptive() if use_descriptive else None
+    desc_templates = (desc["HIER_DESC_TEMPLATES"] if use_hierarchy else desc["DESC_TEMPLATES"]) if desc else []
+    if use_descriptive and len(base_templates) != len(desc_templates):
+        raise ValueError(
+            "Descriptive templates enabled but template counts differ: "
+            f"{len(desc_templates)} (descriptive) vs {len(base_templates)} (base). "
+            "Please make them consistent.")
+    templates_per_class = len(desc_templates) if use_descriptive else len(base_templates)
     prompts = []
-    for name, l2 in _L3:
+    for name, l2_id in _L3:
         l3 = name.replace("_", " ")
-        if use_hierarchy:
-            prompts.append(f"a habitat photo of {L2_NAMES[l2]}, specifically {l3}")
+        l2 = L2_NAMES[l2_id]
+        attrs = desc["DESCRIPTIVE_L3_ATTRS"].get(l3) if desc else None
+        if attrs is not None:
+            text = ", ".join(attrs.values())
+            cls = [t.format(l2=l2, l3=l3, attrs=text) if use_hierarchy else t.format(habitat=l3, attrs=text)
+                   for t in desc_templates]
+        elif use_hierarchy:
+            cls = [t.format(l3=l3, l2=l2) for t in base_templates]
         else:
-            prompts.extend(t.format(l3) for t in CS_TEMPLATES)
-    return prompts, 1
+            cls = [t.format(l3) for t in base_templates]
+        if use_descriptive:
+            print(f"[gen_prompts] {l3}: {cls[:min(2, len(cls))]}")
+        prompts.extend(cls)
+    return prompts, templates_per_class

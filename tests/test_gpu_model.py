@@ -275,3 +275,33 @@ def test_layernorm_fold_with_outlier_activations(tmp_path, cuda_device, monkeypa
     assert cosine(out["1"], ref).min() >= 0.999 and cosine(out["0"], ref).min() >= 0.999
     assert err_plain <= 1e-2
     assert err_fold <= 1e-2
+
+
+def test_engine_lifecycle_and_bf16_warning(tmp_path, cuda_device):
+    """In-place `.data` writes do not bump `_version`: invalidate_engine() makes the next forward repack; updating
+    visual.proj never rebuilds the engine; selecting bf16 operands warns that they are outside the parity tolerance;
+    deepcopy after a forward works."""
+    import copy
+    import warnings
+    geom = GEOMETRIES["ViT-tiny/16"]
+    _, model, preprocess = load_model(tmp_path, geom.name, 0, cuda_device)
+    model.float()
+    x = preprocess.batch_u8(torch.from_numpy(synthetic_images_u8(3, 64)).to(cuda_device))
+    f0 = model.encode_image(x)
+    eng = model.visual._engine
+    model.visual.proj.data.mul_(2.0)
+    with torch.no_grad():
+        model.visual.proj.add_(1.0)
+    assert torch.equal(model.encode_image(x), f0) and model.visual._engine is eng      # proj is not engine state
+    model.visual.ln_post.weight.data.mul_(2.0)           # .data write: invisible to the fingerprint ...
+    assert torch.equal(model.encode_image(x), f0)
+    model.visual.invalidate_engine()                      # ... until the engine is invalidated
+    f1 = model.encode_image(x)
+    assert not torch.equal(f1, f0)
+    twin = copy.deepcopy(model)
+    assert torch.equal(twin.encode_image(x), f1)
+    model.visual.compute_dtype = "bf16"
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        model.encode_image(x)
+    assert any("outside the parity" in str(i.message).lower() or "OUTSIDE the parity" in str(i.message) for i in w)

@@ -32,8 +32,25 @@ def test_label_data_matches_reference(meta):
     assert CS_CLASSNAMES == meta["classnames"] and CS_TEMPLATES == meta["templates"]
     l3_to_l2, l2_names = build_l3_to_l2_map()
     assert l3_to_l2 == meta["l3_to_l2"] and l2_names == meta["l2_names"]
-    assert list(gen_prompts(False)) == meta["gen_prompts_flat"]
-    assert list(gen_prompts(True)) == meta["gen_prompts_hier"]
+    assert list(gen_prompts(False, False)) == meta["gen_prompts_flat"]
+    assert list(gen_prompts(True, False)) == meta["gen_prompts_hier"]
+
+
+def test_gen_prompts_all_modes_match_reference(capsys):
+    """data/templates.py:236-297 incl. the descriptive-attribute prompts (a T1 input the reference supports), against
+    outputs of the reference's own gen_prompts (tools/export_prompt_data.py -> tests/golden/reference_prompts.json):
+    prompts, templates_per_class and the printed per-class preview."""
+    import json
+    from pathlib import Path
+    gold = json.loads((Path(__file__).resolve().parent / "golden" / "reference_prompts.json").read_text())
+    for h in (True, False):
+        for d in (True, False):
+            prompts, tpc = gen_prompts(use_hierarchy=h, use_descriptive=d)
+            g = gold[f"hier={h},desc={d}"]
+            assert prompts == g["prompts"] and tpc == g["templates_per_class"]
+            assert capsys.readouterr().out == g["stdout"]
+    assert gen_prompts() == (gold["hier=True,desc=True"]["prompts"], 1)   # the reference's defaults
+    capsys.readouterr()
 
 
 def _have_vocab():
@@ -244,3 +261,24 @@ def test_reference_archive_is_the_unmodified_reference():
             assert z.read(rel) == (build_ref.REF_SRC / rel).read_bytes(), rel
     ignored = (Path(__file__).resolve().parent.parent / ".gitignore").read_text()
     assert "oracle/_ref/" in ignored
+
+
+def test_model_object_copies_and_engine_fingerprint():
+    """the engine fingerprint excludes visual.proj (the engine never reads it); deepcopy / pickle of a model
+    work (the ctypes handle is not carried); parameter replacement (.float()) refreshes the cached parameter list."""
+    import copy
+    import pickle
+    import torch
+    from aihab_clip_b200.clip.model import build_model
+    from aihab_clip_b200.weights import make_state_dict
+    m = build_model(make_state_dict("ViT-tiny/16", 0))
+    ps = m.visual._engine_params()
+    assert all(p is not m.visual.proj for p in ps) and len(ps) == len(list(m.visual.parameters())) - 1
+    m.float()
+    assert m.visual._engine_params()[0].dtype == torch.float32          # refreshed after _apply
+    m2 = copy.deepcopy(m)
+    assert m2.visual._engine is None and torch.equal(m2.visual.conv1.weight, m.visual.conv1.weight)
+    m3 = pickle.loads(pickle.dumps(m))
+    assert torch.equal(m3.visual.proj, m.visual.proj)
+    m.visual.invalidate_engine()
+    assert m.visual._engine is None

@@ -12,6 +12,6 @@ for f in gemm_tcgen05 attention_tcp; do
   nvcc $FLAGS "$@" -c $f.cu -o build/var_$NAME/$f.o &
 done
 wait
-for f in elementwise attention attention_tc attention_tcf score preprocess api; do OBJS="$OBJS build/$f.o"; done
+for f in elementwise attention attention_tcf score preprocess api; do OBJS="$OBJS build/$f.o"; done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../ab/lib_$NAME.so build/var_$NAME/*.o $OBJS -cudart static
 echo ab/lib_$NAME.so
