@@ -342,6 +342,8 @@ struct aihab_vit {
   CUtensorMap m_y2;
   CUtensorMap m_patches, m_y, m_h, m_x;  // m_x: fp32 residual stream, {32,32} boxes (EPI_BIAS_RES_32)
   CUtensorMap m_attn_q, m_attn_kv;       // qkv view [cap_rows, 3D] of `big` for the tcgen05 attention
+  CUtensorMap m_attn_out3;               // attention output `y` as [max_batch][L][D] (dual-stream kernel's TMA stores)
+  bool has_attn_out3 = false;
   int attn_kind = 0;
   int causal = 0;  // text tower: key j visible to query i only for j <= i (clip/model.py:323-329)
   // text tower ends (aihab_text_*): embedding table, ln_final, EOT rows
@@ -514,7 +516,7 @@ int run_blocks(aihab_vit* h, int n, cudaStream_t s) {
       }
       else if (h->attn_kind == 2)
         CKL(aihab::launch_attention_tcp(h->m_attn_q, h->m_attn_kv, h->y, n, L, h->cfg.heads, h->bf16, h->num_sms, s,
-                                        next_dir(), h->causal));
+                                        next_dir(), h->causal, h->has_attn_out3 ? &h->m_attn_out3 : nullptr));
       else
         CKL(aihab::launch_attention(h->big, h->y, n, L, h->cfg.heads, h->bf16, s));
     }
@@ -640,6 +642,13 @@ int build_stack(aihab_vit* h, int layers, const aihab_vit_block_weights* blocks,
                                   attention_key_box(h->attn_kind, L), h->bf16) != cudaSuccess) {
       fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the attention views");
       return 1;
+    }
+    if (h->attn_kind == 2 && !h->causal && aihab::attention_tcd_supported(L)) {
+      if (aihab::make_tmap_3d_16bit_seq(&h->m_attn_out3, h->y, h->cap_rows / L, L, D, 32, h->bf16) != cudaSuccess) {
+        fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the attention output view");
+        return 1;
+      }
+      h->has_attn_out3 = true;
     }
   }
   return 0;
@@ -1271,8 +1280,13 @@ int aihab_attention(const void* qkv, void* out, int n, int L, int H, int dtype, 
     CK(aihab::make_tmap_2d_16bit(&mkv, qkv, rows, 3 * H * 64, pitch, attention_key_box(kind, L), bf16));
     if (kind == 3)
       CKL(aihab::launch_attention_tcf(mq, mkv, qkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream)));
-    else
-      CKL(aihab::launch_attention_tcp(mq, mkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream)));
+    else {
+      CUtensorMap mo;
+      const bool dual = aihab::attention_tcd_supported(L);
+      if (dual) CK(aihab::make_tmap_3d_16bit_seq(&mo, out, n, L, H * 64, 32, bf16));
+      CKL(aihab::launch_attention_tcp(mq, mkv, out, n, L, H, bf16, sm_count(device_of(qkv)), static_cast<cudaStream_t>(stream), 0,
+                                      0, dual ? &mo : nullptr));
+    }
     return 0;
   }
   CKL(aihab::launch_attention(qkv, out, n, L, H, dtype == AIHAB_BF16, static_cast<cudaStream_t>(stream)));

@@ -361,11 +361,14 @@ bool attention_tcp_supported(int L) {
 int attention_tcp_key_rows(int L) { return (L * attention_tcp_pack(L) + 15) / 16 * 16; }
 
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
-                                 int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse, int causal) {
+                                 int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse, int causal,
+                                 const CUtensorMap* tmap_out3) {
   if (n_img <= 0) return cudaSuccess;
   if (!attention_tcp_supported(L)) return cudaErrorInvalidValue;
   const int g = attention_tcp_pack(L);
   if (g > 1 && causal) return cudaErrorInvalidValue;  // the text tower has L = 77
+  if (g == 1 && !causal && tmap_out3 != nullptr && attention_tcd_supported(L))  // two query tiles per unit: dual-stream kernel
+    return launch_attention_tcd(tmap_q, tmap_kv, *tmap_out3, n_img, L, H, is_bf16, num_sms, stream, reverse);
   const int Ls = g * L;                       // rows per sequence
   const int n_seq = (n_img + g - 1) / g;
   const int Lk = (Ls + 15) / 16 * 16;

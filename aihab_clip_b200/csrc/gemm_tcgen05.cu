@@ -650,6 +650,25 @@ cudaError_t make_tmap_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+cudaError_t make_tmap_3d_16bit_seq(CUtensorMap* map, const void* base, uint64_t n_seq, uint64_t seq_rows, uint64_t cols,
+                                   uint32_t box_rows, int ab_format) {
+  if (g_encode == nullptr) {
+    cudaError_t e = gemm_init();
+    if (e != cudaSuccess) return e;
+  }
+  if (((cols * 2) & 15) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || box_rows > 256 || n_seq == 0)
+    return cudaErrorInvalidValue;
+  cuuint64_t gdim[3] = {cols, seq_rows, n_seq};
+  cuuint64_t gstride[2] = {cols * 2, seq_rows * cols * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, ab_format ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 int gemm_block_n(int M, int N, int num_sms) {
   if (N <= 128) return 128;
   const long m_blocks = (M + BM - 1) / BM;

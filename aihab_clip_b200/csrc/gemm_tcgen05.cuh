@@ -68,6 +68,12 @@ struct GemmParams {
 cudaError_t make_tmap_2d_16bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                                uint64_t row_pitch_bytes, uint32_t box_rows, int ab_format);
 
+// 3-D map over a 16-bit activation buffer viewed as [n_seq][seq_rows][cols] (row-major, sequences back to back) with a
+// {64 cols, box_rows, 1} box and SWIZZLE_128B: a store of a row block that runs past seq_rows is clipped at the end
+// of ITS sequence (the attention epilogue's partial last query tile).
+cudaError_t make_tmap_3d_16bit_seq(CUtensorMap* map, const void* base, uint64_t n_seq, uint64_t seq_rows, uint64_t cols,
+                                   uint32_t box_rows, int ab_format);
+
 // Tensor map over the fp32 residual stream [rows, cols] with a {32 cols, 32 rows} box (4 KB) and SWIZZLE_128B:
 // used by EPI_BIAS_RES_32 to load, and store back in place, the residual slice of every epilogue warp.
 cudaError_t make_tmap_2d_f32_box32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,

@@ -42,8 +42,18 @@ bool attention_tcp_supported(int L);
 int attention_tcp_pack(int L);      // images per packed sequence (1 for L > 64)
 int attention_tcp_key_rows(int L);  // rows of the K / V TMA box
 // causal != 0: key j is visible to query i only if j <= i (the text tower's attn_mask, clip/model.py:323-329).
+// tmap_out3 (optional): 3-D output map for the dual-stream kernel; without it the single-stream kernel runs.
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
-                                 int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse = 0, int causal = 0);
+                                 int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse = 0, int causal = 0,
+                                 const CUtensorMap* tmap_out3 = nullptr);
+
+// Dual-stream variant for 128 < L <= 224 (the two 128-row query tiles of an (image, head) unit as two streams with one
+// softmax thread per row, K / V shared in smem; attention_tcd.cu).  Same tensor maps as launch_attention_tcp; used by it
+// for unmasked sequences unless AIHAB_ATTN_DUAL=0.
+bool attention_tcd_supported(int L);
+// tmap_out: make_tmap_3d_16bit_seq over out viewed as [n_img][L][H * 64] with a 32-row box.
+cudaError_t launch_attention_tcd(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, const CUtensorMap& tmap_out,
+                                 int n_img, int L, int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse = 0);
 
 // Persistent flash-style variant for long sequences (128 < L <= 1024; ViT-L/14: 257, ViT-L/14@336px: 577): keys in
 // blocks of <= 160 with an online softmax, O rescaled in TMEM only when the running max moves by more than 2^8.

@@ -8,7 +8,7 @@ NAME=$1; shift
 mkdir -p ../../ab build/var_$NAME
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden"
 OBJS=""
-for f in gemm_tcgen05 attention_tcp; do
+for f in gemm_tcgen05 attention_tcp attention_tcd; do
   nvcc $FLAGS "$@" -c $f.cu -o build/var_$NAME/$f.o &
 done
 wait
