@@ -79,7 +79,16 @@ constexpr int STG_BYTES = 8 * 4096;  // O staging: one 32-row x 128 B SWIZZLE_12
 __host__ __device__ constexpr int smem_bytes(int Lk) { return NSTG * st_bytes(Lk) + STG_BYTES + BAR_BYTES + 1024; }
 constexpr int SMEM_CAP = 227 * 1024;
 constexpr int TM_STREAM = 256;  // TMEM columns per stream
-constexpr int TM_O = 128;       // O inside the stream's buffer
+constexpr int P_SPLIT = 4;      // 32-key chunks of P handed to the PV MMA early (while the exp2 pass does the rest)
+// Column plan inside a stream's 256 TMEM columns.  Everything that is written while the exp2 pass still reads S must
+// land on columns whose S values are already consumed (chunks are read in ascending order) or on the spare columns
+// behind S.  EARLY plan (Lk <= 208, more than P_SPLIT chunks): P of chunks 0..2 -> spare [208, 256), P of chunk c >= 3
+// -> [16 (c - 3), ...) inside S chunks 0, 1, O -> [64, 128) = S chunks 2, 3: after chunk 3 the PV MMAs over the first
+// four chunks may run while chunks 4.. are still being read.  PLAIN plan: P of chunk c -> [16 c, ...), O -> [128, 192),
+// PV only after the whole row is done.
+__host__ __device__ constexpr bool plan_early(int Lk) { return Lk <= 208 && (Lk >> 5) > P_SPLIT; }
+__device__ __forceinline__ int p_col(bool early, int c) { return early ? (c < 3 ? 208 + 16 * c : 16 * (c - 3)) : 16 * c; }
+__device__ __forceinline__ int o_col(bool early) { return early ? 64 : 128; }
 static_assert(smem_bytes(224) <= SMEM_CAP, "smem budget");
 static_assert(st_v(144) % 1024 == 0 && st_bytes(144) % 1024 == 0, "SWIZZLE_128B tiles need 1024 B alignment");
 
@@ -97,11 +106,12 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* bar_kfree = bars + 4;    // [NSTG] both streams' S MMAs of the stage retired: Q0, Q1, K may be overwritten
   uint64_t* bar_vfree = bars + 16;   // [NSTG] both streams' PV MMAs of the stage retired: V may be overwritten
   uint64_t* bar_turn = bars + 18;    // [2][4] exp2-phase token of stream g, quadrant q
+  uint64_t* bar_p1 = bars + 26;      // [2] first P_SPLIT key chunks of P written: the PV MMAs over them may start
   uint64_t* bar_sfull = bars + 6;    // [2] S of stream g written
   uint64_t* bar_p = bars + 8;        // [2] P of stream g written to TMEM (4 warp arrivals)
   uint64_t* bar_o = bars + 10;       // [2] O of stream g written
   uint64_t* bar_bfree = bars + 12;   // [2] O of stream g read: its TMEM buffer is free for the next S (4 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
@@ -131,6 +141,7 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ptx::mbar_init(&bar_p[i], 4);
       ptx::mbar_init(&bar_o[i], 1);
       ptx::mbar_init(&bar_bfree[i], 4);
+      ptx::mbar_init(&bar_p1[i], 4);
     }
     ptx::fence_mbar_init();
   }
@@ -186,14 +197,28 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ptx::umma_commit_w(&bar_sfull[g]);
       ptx::umma_commit_w(&bar_kfree[s]);
       TSTAMP(g, 3);
+      // O = P V in two instalments: the k-steps of the first P_SPLIT chunks as soon as they are in TMEM (the softmax
+      // is still in its exp2 pass over the remaining keys), the rest after the full hand-off
+      const uint32_t v_base = st + ST_V;
+      const bool early = plan_early(Lk);
+      const int k_early = early ? 2 * P_SPLIT : 0;
+      const uint32_t t_o = tbuf + o_col(early);
+      if (k_early) {
+        ptx::mbar_wait(&bar_p1[g], u & 1);
+        ptx::mbar_wait(&bar_v[s], ks & 1);
+        ptx::tc_fence_after();
+        for (int j = 0; j < k_early; ++j) {
+          const uint64_t vd = ptx::make_mnmajor_sw128_desc(v_base + j * 2048);
+          ptx::umma_f16_ts_w(t_o, tbuf + p_col(early, j >> 1) + (j & 1) * 8, vd, idesc_o, j != 0);  // A = P from TMEM
+        }
+      }
       ptx::mbar_wait(&bar_p[g], u & 1);
       TSTAMP(g, 4);
       ptx::mbar_wait(&bar_v[s], ks & 1);
       ptx::tc_fence_after();
-      const uint32_t v_base = st + ST_V;
-      for (int j = 0; j < ksteps; ++j) {
+      for (int j = k_early; j < ksteps; ++j) {
         const uint64_t vd = ptx::make_mnmajor_sw128_desc(v_base + j * 2048);
-        ptx::umma_f16_ts_w(tbuf + TM_O, tbuf + j * 8, vd, idesc_o, j != 0);  // A = P from TMEM
+        ptx::umma_f16_ts_w(t_o, tbuf + p_col(early, j >> 1) + (j & 1) * 8, vd, idesc_o, j != 0);  // A = P from TMEM
       }
       ptx::umma_commit_w(&bar_o[g]);
       ptx::umma_commit_w(&bar_vfree[s]);
@@ -208,6 +233,7 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const float sl2 = 0.125f * 1.4426950408889634f;
     const int n32 = Lk >> 5;
     const bool tail16 = (Lk & 31) != 0;
+    const bool early = plan_early(Lk);
 
     for (int u = 0; u < n_units; ++u) {
       int img, h;
@@ -217,11 +243,14 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ptx::tc_fence_after();
       if (quad == 0) TSTAMP(2 + g, 1);
       float l = 0.f;
+      uint32_t buf[96];
       if (has_rows) {
-        // ---- pass 1: row maximum over the valid key columns [0, L); the TMEM load of chunk c+1 is in flight while
-        // chunk c is reduced (two register buffers, tmem_ld_wait_regs names the buffer it completes)
+        // ---- pass 1: row maximum over the valid key columns [0, L)
         float m0 = -INFINITY, m1 = -INFINITY;
-        uint32_t ra[32], rb[32];
+        // ONE register buffer for every phase of the item (3 chunks in the max pass, 2 in the exp2 pass, the 64 O values
+        // in the epilogue), so that the phases do not add up in the allocator
+        uint32_t (&ra)[32] = reinterpret_cast<uint32_t(&)[32]>(buf[0]);
+        uint32_t (&rb)[32] = reinterpret_cast<uint32_t(&)[32]>(buf[32]);
         auto max32 = [&](const uint32_t (&r)[32], int c) {
           if (c * 32 + 32 <= L) {
 #pragma unroll
@@ -235,17 +264,17 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
               if (c * 32 + j < L) m0 = fmaxf(m0, __uint_as_float(r[j]));
           }
         };
-        if (!(AIHAB_ATTN_EXPERIMENT & 16)) ptx::tmem_ld_32x32(t_row, ra);
+        // three tcgen05.ld.x32 in flight per wait: the pass is bound by the TMEM load latency, not by its 208 FMNMX
 #pragma unroll 1
-        for (int c = 0; c < ((AIHAB_ATTN_EXPERIMENT & 16) ? 0 : n32); c += 2) {
-          ptx::tmem_ld_wait_regs(ra);
+        for (int c = 0; c < ((AIHAB_ATTN_EXPERIMENT & 16) ? 0 : n32); c += 3) {
+          uint32_t (&rc)[32] = reinterpret_cast<uint32_t(&)[32]>(buf[64]);
+          ptx::tmem_ld_32x32(t_row + c * 32, ra);
           if (c + 1 < n32) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, rb);
+          if (c + 2 < n32) ptx::tmem_ld_32x32(t_row + (c + 2) * 32, rc);
+          ptx::tmem_ld_wait();
           max32(ra, c);
-          if (c + 1 < n32) {
-            ptx::tmem_ld_wait_regs(rb);
-            if (c + 2 < n32) ptx::tmem_ld_32x32(t_row + (c + 2) * 32, ra);
-            max32(rb, c + 1);
-          }
+          if (c + 1 < n32) max32(rb, c + 1);
+          if (c + 2 < n32) max32(rc, c + 2);
         }
         if (tail16) {
           uint32_t r[16];
@@ -287,7 +316,7 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             pk[j] = ptx::pack2<BF16>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
             pk[j + 1] = ptx::pack2<BF16>(__uint_as_float(r[2 * j + 2]), __uint_as_float(r[2 * j + 3]));
           }
-          if (!(AIHAB_ATTN_EXPERIMENT & 1)) ptx::tmem_st_32x16(t_row + c * 16, pk);  // 32 keys -> 16 packed columns over S columns already read
+          if (!(AIHAB_ATTN_EXPERIMENT & 1)) ptx::tmem_st_32x16(t_row + p_col(early, c), pk);  // 32 keys -> 16 packed columns
           else l0 += __uint_as_float(pk[0] ^ pk[5] ^ pk[10] ^ pk[15]);
         };
         if (!(AIHAB_ATTN_EXPERIMENT & 2)) ptx::tmem_ld_32x32(t_row, ra);
@@ -304,6 +333,12 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
               if (c + 2 < n32) ptx::tmem_ld_32x32(t_row + (c + 2) * 32, ra);
             }
             exp32(rb, c + 1);
+          }
+          if (c + 2 == P_SPLIT && early) {  // first instalment of P is complete: let its PV MMAs start
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bar_p1[g]);
           }
         }
         if (tail16) {
@@ -322,7 +357,7 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             l1 += p1;
             pk[j] = ptx::pack2<BF16>(p0, p1);
           }
-          ptx::tmem_st_32x8(t_row + n32 * 16, pk);
+          ptx::tmem_st_32x8(t_row + p_col(early, n32), pk);
         }
         if (lane == 0) ptx::mbar_arrive(&bar_turn[(g ^ 1) * 4 + quad]);  // the other stream's turn
         l = (l0 + l1) + (l2 + l3);
@@ -330,6 +365,7 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         ptx::tmem_st_wait();
         if (quad == 0) TSTAMP(2 + g, 5);
       } else {  // a quadrant without rows (second tile, rows >= L) only passes the token on
+        if (early && lane == 0) ptx::mbar_arrive(&bar_p1[g]);
         if (!(AIHAB_ATTN_EXPERIMENT & 8)) ptx::mbar_wait(&bar_turn[g * 4 + quad], (u & 1) ^ (g == 0 ? 1 : 0));
         if (lane == 0) ptx::mbar_arrive(&bar_turn[(g ^ 1) * 4 + quad]);
       }
@@ -341,10 +377,10 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ptx::mbar_wait(&bar_o[g], u & 1);
       ptx::tc_fence_after();
       if (quad == 0) TSTAMP(2 + g, 7);
-      uint32_t o[64];
+      uint32_t (&o)[64] = reinterpret_cast<uint32_t(&)[64]>(buf[0]);
       if (has_rows) {
-        ptx::tmem_ld_32x32(t_row + TM_O, reinterpret_cast<uint32_t(&)[32]>(o[0]));
-        ptx::tmem_ld_32x32(t_row + TM_O + 32, reinterpret_cast<uint32_t(&)[32]>(o[32]));
+        ptx::tmem_ld_32x32(t_row + o_col(early), reinterpret_cast<uint32_t(&)[32]>(o[0]));
+        ptx::tmem_ld_32x32(t_row + o_col(early) + 32, reinterpret_cast<uint32_t(&)[32]>(o[32]));
         ptx::tmem_ld_wait();
       }
       ptx::tc_fence_before();  // O read (wait::ld) before the next S MMA may overwrite the buffer
