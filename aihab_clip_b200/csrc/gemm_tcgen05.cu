@@ -34,9 +34,15 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int kResWarps = epi_warps(EPI_BIAS_RES_32, TWO);  // residual epilogue warps (rings)
-  static constexpr int kRS = 4;  // ring slots per residual epilogue warp
+#ifndef AIHAB_RES_RING
+#define AIHAB_RES_RING 4
+#endif
+#ifndef AIHAB_RES_STAGES
+#define AIHAB_RES_STAGES 4
+#endif
+  static constexpr int kRS = TWO ? AIHAB_RES_RING : 4;  // ring slots per residual epilogue warp (kRS - 1 boxes in flight)
   static constexpr int kStages =
-      TWO ? (kRes ? 4 : 5) : ((BN == 256) ? 3 : (kRes ? 4 : 5));
+      TWO ? (kRes ? AIHAB_RES_STAGES : 5) : ((BN == 256) ? 3 : (kRes ? (AIHAB_RES_STAGES < 4 ? AIHAB_RES_STAGES : 4) : 5));
   static constexpr int kStageBytes = kABytes + kBBytes;
   // residual rings (kResWarps x kRS boxes) + 2 KB per warp for the coalesced gamma*x store | 8 warps x 4 KB staging tile
   static constexpr int kStagingBytes = kRes ? kResWarps * (kRS * RES_BOX + 2048) : 8 * 4096;

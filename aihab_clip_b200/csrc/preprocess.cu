@@ -4,6 +4,7 @@
 // ImagingResample for 8-bit images bit for bit: separable, horizontal pass then vertical pass, each pass in
 // 22-bit fixed point with a uint8 round-and-clamp between the passes.  Coefficient tables come from the host
 // (api.cu: build_resample_axis) and are indexed in resized-image coordinates.
+#include <cstdlib>
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -102,6 +103,180 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   }
 }
 
+
+// ---- resize path, round 2 -------------------------------------------------------------------------------------------
+// Same arithmetic as preprocess_kernel (Pillow's two fixed-point passes with the uint8 round-and-clamp in between), laid
+// out for the memory system:
+//   1. the input rows a strip of TH2 output rows needs are ONE contiguous byte range of the image: staged in shared
+//      memory with 16-byte loads (the old kernel issued one global byte load per tap);
+//   2. horizontal pass: a thread owns one output column - its taps' first index, count and coefficients stay in
+//      registers for every row of the strip - and reads its <= KMAX-pixel window from shared memory;
+//   3. vertical pass + normalise: a thread produces two adjacent output pixels of one channel and stores them together.
+constexpr int TH2 = 16;
+constexpr int KMAX = 12;
+
+template <typename OutT>
+__device__ __forceinline__ void store2(OutT* dst, float a, float b);
+template <>
+__device__ __forceinline__ void store2<float>(float* dst, float a, float b) { *reinterpret_cast<float2*>(dst) = make_float2(a, b); }
+template <>
+__device__ __forceinline__ void store2<__half>(__half* dst, float a, float b) { *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(a, b); }
+template <>
+__device__ __forceinline__ void store2<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a, b);
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store4(OutT* dst, const float (&f)[4]);
+template <>
+__device__ __forceinline__ void store4<float>(float* dst, const float (&f)[4]) {
+  *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <>
+__device__ __forceinline__ void store4<__half>(__half* dst, const float (&f)[4]) {
+  uint2 v;
+  v.x = ptx::pack2<false>(f[0], f[1]);
+  v.y = ptx::pack2<false>(f[2], f[3]);
+  *reinterpret_cast<uint2*>(dst) = v;
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* dst, const float (&f)[4]) {
+  uint2 v;
+  v.x = ptx::pack2<true>(f[0], f[1]);
+  v.y = ptx::pack2<true>(f[2], f[3]);
+  *reinterpret_cast<uint2*>(dst) = v;
+}
+
+// Shared-memory traffic is the limit of this kernel (one LDS per warp instruction, whatever its width), so both passes
+// read 32-bit words and pick the bytes apart in registers:
+//   pass 1: a thread's tap window (<= KMAX pixels = 36 bytes) is loaded as ten aligned words and re-aligned with funnel
+//           shifts (its byte offset is the same for every row of the strip); the result goes to a CHANNEL-PLANAR tile;
+//   pass 2: a thread produces four consecutive pixels of one channel: one word per tap from the planar tile.
+template <typename OutT>
+__global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ in_end,
+                                                                int sh, int sw, int R, ResampleTables t, OutT* __restrict__ out,
+                                                                int layout, int p, int Kpad, int in_cap, int rows_cap) {
+  extern __shared__ __align__(16) uint8_t smem2[];
+  uint8_t* sin = smem2;             // staged input bytes (16-byte aligned window around the strip's rows) + 48 B of slack
+  uint8_t* tile = smem2 + in_cap;   // [3][rows_cap][R] horizontally resampled rows, channel-planar, crop columns only
+  const int img = blockIdx.y;
+  const int y0 = blockIdx.x * TH2;
+  const int th = min(TH2, R - y0);
+  const uint8_t* src = in + static_cast<size_t>(img) * sh * sw * 3;
+  int r_first, r_last;
+  if (t.need_v) {
+    const int ry0 = t.crop_top + y0, ry1 = t.crop_top + y0 + th - 1;
+    r_first = t.v_bounds[2 * ry0];
+    r_last = t.v_bounds[2 * ry1] + t.v_bounds[2 * ry1 + 1];
+  } else {
+    r_first = t.crop_top + y0;
+    r_last = r_first + th;
+  }
+  const int nrows = r_last - r_first;
+  const int row_bytes = sw * 3;
+  const int plane = rows_cap * R;
+  // ---- stage [r_first, r_last) x sw x 3 bytes
+  const uint8_t* g0 = src + static_cast<size_t>(r_first) * row_bytes;
+  const uint8_t* g1 = src + static_cast<size_t>(r_last) * row_bytes;
+  const uint8_t* a0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g0) & ~static_cast<uintptr_t>(15));
+  const int head = static_cast<int>(g0 - a0);
+  const int nvec = static_cast<int>((g1 - a0 + 15) >> 4);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint8_t* gp = a0 + (static_cast<size_t>(i) << 4);
+    if (gp >= in && gp + 16 <= in_end) {
+      reinterpret_cast<uint4*>(sin)[i] = __ldg(reinterpret_cast<const uint4*>(gp));
+    } else {  // first / last vector of the whole batch buffer
+      for (int b = 0; b < 16; ++b) sin[(i << 4) + b] = (gp + b >= in && gp + b < in_end) ? __ldg(gp + b) : 0;
+    }
+  }
+  __syncthreads();
+  // ---- pass 1: horizontal
+  for (int ox = threadIdx.x; ox < R; ox += blockDim.x) {
+    const int rx = t.crop_left + ox;
+    int xmin = rx, cnt = 1;
+    int k[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) k[j] = 0;
+    k[0] = 1 << 22;  // no horizontal resize: the pixel itself (4194304 * v + 2^21) >> 22 == v
+    if (t.need_h) {
+      xmin = t.h_bounds[2 * rx];
+      cnt = t.h_bounds[2 * rx + 1];
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) k[j] = j < cnt ? __ldg(t.h_coeffs + static_cast<size_t>(rx) * t.h_ksize + j) : 0;
+    }
+    const int nw = (3 * cnt + 3) >> 2;        // words of window bytes after re-alignment
+    for (int r = 0; r < nrows; ++r) {
+      const int off = head + r * row_bytes + xmin * 3;
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(sin + (off & ~3));
+      const int sh8 = (off & 3) * 8;
+      uint32_t w[KMAX * 3 / 4 + 1];
+#pragma unroll
+      for (int i = 0; i < KMAX * 3 / 4 + 1; ++i) w[i] = i <= nw ? wp[i] : 0u;
+#pragma unroll
+      for (int i = 0; i < KMAX * 3 / 4; ++i) w[i] = __funnelshift_r(w[i], w[i + 1], sh8);  // window byte b = byte b of w[]
+      int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        if (j < cnt) {
+          s0 += static_cast<int>((w[(3 * j) >> 2] >> (((3 * j) & 3) * 8)) & 0xffu) * k[j];
+          s1 += static_cast<int>((w[(3 * j + 1) >> 2] >> (((3 * j + 1) & 3) * 8)) & 0xffu) * k[j];
+          s2 += static_cast<int>((w[(3 * j + 2) >> 2] >> (((3 * j + 2) & 3) * 8)) & 0xffu) * k[j];
+        }
+      }
+      uint8_t* o = tile + r * R + ox;
+      o[0] = static_cast<uint8_t>(clip8(s0));
+      o[plane] = static_cast<uint8_t>(clip8(s1));
+      o[2 * plane] = static_cast<uint8_t>(clip8(s2));
+    }
+  }
+  __syncthreads();
+  // ---- pass 2: vertical + normalise, four consecutive pixels of one channel per thread
+  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+  const int g = (layout == 1) ? R / p : 0;
+  const int quads = R >> 2;
+  for (int idx = threadIdx.x; idx < th * 3 * quads; idx += blockDim.x) {
+    const int oy = idx / (3 * quads);
+    const int rem = idx - oy * 3 * quads;
+    const int c = rem / quads, ox = (rem - c * quads) * 4;
+    int s[4] = {1 << 21, 1 << 21, 1 << 21, 1 << 21};
+    const uint8_t* col = tile + c * plane + ox;
+    if (t.need_v) {
+      const int ry = t.crop_top + y0 + oy;
+      const int ymin = t.v_bounds[2 * ry] - r_first, cnt = t.v_bounds[2 * ry + 1];
+      const int* kk = t.v_coeffs + static_cast<size_t>(ry) * t.v_ksize;
+      for (int j = 0; j < cnt; ++j) {
+        const int kj = __ldg(kk + j);
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(col + (ymin + j) * R);
+        s[0] += static_cast<int>(w & 0xffu) * kj;
+        s[1] += static_cast<int>((w >> 8) & 0xffu) * kj;
+        s[2] += static_cast<int>((w >> 16) & 0xffu) * kj;
+        s[3] += static_cast<int>(w >> 24) * kj;
+      }
+    } else {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(col + oy * R);
+      s[0] += static_cast<int>(w & 0xffu) << 22;
+      s[1] += static_cast<int>((w >> 8) & 0xffu) << 22;
+      s[2] += static_cast<int>((w >> 16) & 0xffu) << 22;
+      s[3] += static_cast<int>(w >> 24) << 22;
+    }
+    float f[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = (static_cast<float>(clip8(s[q])) / 255.0f - mean[c]) / stdv[c];
+    const int y = y0 + oy;
+    if (layout == 0) {
+      store4<OutT>(out + ((static_cast<size_t>(img) * 3 + c) * R + y) * R + ox, f);
+    } else {  // im2col rows: a pixel quad can straddle two patches when p % 4 != 0 -> two pairs
+      const int gy = y / p, ky = y - gy * p;
+#pragma unroll
+      for (int q = 0; q < 4; q += 2) {
+        const int gx = (ox + q) / p, kx = (ox + q) - gx * p;
+        store2<OutT>(out + (static_cast<size_t>(img) * g * g + gy * g + gx) * Kpad + c * p * p + ky * p + kx, f[q], f[q + 1]);
+      }
+    }
+  }
+}
+
 // ToTensor + Normalize of one uint8: (x / 255 - mean) / std with both divisions correctly rounded, as torchvision's
 // fp32 tensor ops evaluate it, but without the division sequence: q = a * RN(1/b), r = fma(-b, q, a), q' = fma(r, RN(1/b), q)
 // is the correctly rounded quotient (Markstein); checked exhaustively for the 256 x 3 possible inputs against IEEE
@@ -141,10 +316,19 @@ __global__ void __launch_bounds__(256) normalize_im2col16_kernel(const uint8_t* 
       strip[i] = __ldg(src0 + r * row_pitch + (i - r * RC));
     }
   }
+  // (x / 255 - mean) / std has 256 x 3 possible results: a shared-memory table of the 16-bit outputs (computed with
+  // the exact arithmetic of normalize_u8) replaces ~10 FP instructions per byte by one 16-bit shared-memory load
+  __shared__ uint16_t lut[3][256];
+  {
+    const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+    const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+    const float rstd[3] = {1.0f / 0.26862954f, 1.0f / 0.26130258f, 1.0f / 0.27577711f};
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+      const int c = i >> 8;
+      lut[c][i & 255] = static_cast<uint16_t>(ptx::pack2<BF16>(normalize_u8(i & 255, mean[c], stdv[c], rstd[c]), 0.f) & 0xffffu);
+    }
+  }
   __syncthreads();
-  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
-  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
-  const float rstd[3] = {1.0f / 0.26862954f, 1.0f / 0.26130258f, 1.0f / 0.27577711f};
   const int kx8n = p >> 3;              // 8-pixel groups per patch row
   const int groups = g * p * kx8n;      // 8-pixel groups of the strip
   uint16_t* dst0 = out + (static_cast<size_t>(img) * g + gy) * g * 3 * p * p;
@@ -167,8 +351,7 @@ __global__ void __launch_bounds__(256) normalize_im2col16_kernel(const uint8_t* 
       uint32_t pk[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        pk[j] = ptx::pack2<BF16>(normalize_u8(byte_at(6 * j + c), mean[c], stdv[c], rstd[c]),
-                                 normalize_u8(byte_at(6 * j + 3 + c), mean[c], stdv[c], rstd[c]));
+        pk[j] = static_cast<uint32_t>(lut[c][byte_at(6 * j + c)]) | (static_cast<uint32_t>(lut[c][byte_at(6 * j + 3 + c)]) << 16);
       *reinterpret_cast<uint4*>(dst0 + (gx * 3 + c) * p * p + ky * p + kx8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
@@ -197,6 +380,21 @@ cudaError_t launch_t(const uint8_t* in, int n, int sh, int sw, int R, const Resa
   }
   dim3 grid((R + TH - 1) / TH, n);
   preprocess_kernel<OutT><<<grid, 256, smem, stream>>>(in, sh, sw, R, t, static_cast<OutT*>(out), layout, p, Kpad);
+  return cudaGetLastError();
+}
+
+
+template <typename OutT>
+cudaError_t launch_resize_t(const uint8_t* in, int n, int sh, int sw, int R, const ResampleTables& t, void* out, int layout,
+                            int p, int Kpad, int rows_in, cudaStream_t stream) {
+  const int in_cap = ((rows_in * sw * 3 + 15 + 16 + 48) / 16) * 16;  // staged bytes incl. the alignment head + window slack
+  const size_t smem = static_cast<size_t>(in_cap) + static_cast<size_t>(rows_in) * R * 3;
+  cudaError_t e = cudaFuncSetAttribute(preprocess_resize_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  dim3 grid((R + TH2 - 1) / TH2, n);
+  preprocess_resize_kernel<OutT><<<grid, 256, smem, stream>>>(in, in + static_cast<size_t>(n) * sh * sw * 3, sh, sw, R, t,
+                                                              static_cast<OutT*>(out), layout, p, Kpad, in_cap, rows_in);
   return cudaGetLastError();
 }
 
@@ -230,6 +428,25 @@ cudaError_t launch_preprocess(const uint8_t* in, int n, int sh, int sw, int R, c
   if (layout == 1 && Kpad > 3 * p * p) {
     const long rows = static_cast<long>(n) * (R / p) * (R / p);
     zero_pad_kernel<<<148, 256, 0, stream>>>(static_cast<uint16_t*>(out), rows, 3 * p * p, Kpad);
+  }
+  // the shared-memory staged resize kernel: even R (pixel pairs), taps that fit the register window, strip fits smem
+  if ((R & 3) == 0 && (!t.need_h || t.h_ksize <= KMAX) && (layout == 0 || (p & 1) == 0) &&
+      getenv("AIHAB_PREPROCESS_LEGACY") == nullptr) {
+    int rows_in = TH2;
+    if (t.need_v) {
+      const int scale_up = (sh + t.new_h - 1) / t.new_h;
+      rows_in = TH2 * scale_up + t.v_ksize + 2;
+      if (rows_in > sh) rows_in = sh;
+    }
+    const size_t need = static_cast<size_t>(rows_in) * sw * 3 + 96 + static_cast<size_t>(rows_in) * R * 3;
+    if (need <= 112 * 1024) {
+      switch (out_dtype) {
+        case 0: return launch_resize_t<float>(in, n, sh, sw, R, t, out, layout, p, Kpad, rows_in, stream);
+        case 1: return launch_resize_t<__half>(in, n, sh, sw, R, t, out, layout, p, Kpad, rows_in, stream);
+        case 2: return launch_resize_t<__nv_bfloat16>(in, n, sh, sw, R, t, out, layout, p, Kpad, rows_in, stream);
+        default: return cudaErrorInvalidValue;
+      }
+    }
   }
   switch (out_dtype) {
     case 0: return launch_t<float>(in, n, sh, sw, R, t, out, layout, p, Kpad, max_rows, stream);
