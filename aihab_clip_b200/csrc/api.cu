@@ -1072,7 +1072,14 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
   keep_pool_warm(dev);
   const int bf16 = dtype == AIHAB_BF16;
   const int sms = sm_count(dev);
-  const int chunk = 32768;
+  // rows per pass (AIHAB_SCORE16_CHUNK overrides).  Measured on B200 for 1 M x 768 -> 512 -> 1000 classes, top-5:
+  // 32768 rows 9.5 ms, 16384 10.3, 8192 11.4, 4096 15.5 - L2-sized passes do NOT pay: the five launches per pass are
+  // bound by their own latency / wave quantisation, not by the HBM round trip of the intermediates.
+  static const int chunk_env = [] {
+    const char* e = getenv("AIHAB_SCORE16_CHUNK");
+    return e ? atoi(e) : 0;
+  }();
+  const int chunk = chunk_env > 0 ? chunk_env : 32768;
   const int rows_tmp = std::min(n, chunk);
   AsyncTemp<uint8_t> projT_t(s), w3_t(s), a3_t(s);
   AsyncTemp<float> emb_raw_t(s), logit_t(s);

@@ -175,6 +175,16 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* _
   const int nrows = r_last - r_first;
   const int row_bytes = sw * 3;
   const int plane = rows_cap * R;
+  // (v / 255 - mean) / std takes 256 x 3 values: tabulated once per CTA with the reference's own two IEEE divisions
+  __shared__ float lutf[3][256];
+  {
+    const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+    const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+      const int c = i >> 8;
+      lutf[c][i & 255] = (static_cast<float>(i & 255) / 255.0f - mean[c]) / stdv[c];
+    }
+  }
   // ---- stage [r_first, r_last) x sw x 3 bytes
   const uint8_t* g0 = src + static_cast<size_t>(r_first) * row_bytes;
   const uint8_t* g1 = src + static_cast<size_t>(r_last) * row_bytes;
@@ -231,8 +241,6 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* _
   }
   __syncthreads();
   // ---- pass 2: vertical + normalise, four consecutive pixels of one channel per thread
-  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
-  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
   const int g = (layout == 1) ? R / p : 0;
   const int quads = R >> 2;
   for (int idx = threadIdx.x; idx < th * 3 * quads; idx += blockDim.x) {
@@ -262,7 +270,7 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* _
     }
     float f[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) f[q] = (static_cast<float>(clip8(s[q])) / 255.0f - mean[c]) / stdv[c];
+    for (int q = 0; q < 4; ++q) f[q] = lutf[c][clip8(s[q])];
     const int y = y0 + oy;
     if (layout == 0) {
       store4<OutT>(out + ((static_cast<size_t>(img) * 3 + c) * R + y) * R + ox, f);
