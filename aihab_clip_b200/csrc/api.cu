@@ -361,6 +361,9 @@ namespace {
 
 int dev_alloc(aihab_vit* h, void** p, size_t bytes) {
   CK(cudaMalloc(p, bytes));
+  // zero once: masked attention keys (padding rows of a 64-row slot, rows behind the last image of a partial batch) are
+  // multiplied by P = 0, which only gives 0 if what they hold is finite
+  CK(cudaMemset(*p, 0, bytes));
   h->allocs.push_back(*p);
   h->ws_bytes += bytes;
   return 0;

@@ -10,10 +10,12 @@
 //                                   16-bit pairs over the S columns (tcgen05.st) - the PV MMA takes A from TMEM, so P
 //                                   never touches shared memory; the O(i-1) epilogue (TMEM -> 1/sum -> global) runs
 //                                   before the hand-off, hiding the PV MMA of the previous item
-// Short sequences (16 <= L <= 64, ViT-B/32: L = 50) are PACKED: g = 128 / L consecutive images of the same head form one
-// "sequence" of g * L rows (they are contiguous rows of the qkv buffer), one S = Q K^T covers all of them and a
-// block-diagonal mask (query row r sees keys [r / L * L, r / L * L + L)) keeps the images apart; P is zero outside the
-// row's own block, so O = P V over the stacked V rows is already the per-image result.
+// Short sequences (16 <= L <= 64, ViT-B/32: L = 50) share a tile TWO AT A TIME in 64-row SLOTS: image a of a pair owns
+// query rows / keys [0, L), image b [64, 64 + L) (two 64-row TMA boxes per operand, the rows in between are padding), one
+// S = Q K^T covers both and a block mask (query row r sees keys [64 (r / 64), 64 (r / 64) + L)) keeps them apart; P is
+// zero outside the row's own slot, so O = P V over both slots is already the per-image result.  Because an image's keys
+// always sit at the same offsets inside the 16-key MMA steps, whichever slot it lands in and whoever its neighbour is,
+// its result is bit-identical for every batch composition (the contiguous packing of round 1 was not, and stayed opt-in).
 // TMEM: S0/P0 [0,224) S1/P1 [224,448) O [448,512).  smem: NS x (Q 16 KB + K Lk x 128 B + V Lk x 128 B), NS = 2..4.
 // Reference: clip/model.py:179-181 (nn.MultiheadAttention core: softmax(q k^T / sqrt(64)) v, no mask).
 #include "gemm_tcgen05.cuh"
@@ -187,8 +189,19 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const int s = it % NS, k = it / NS;  // input stage and its use count
         uint8_t* st = smem + s * ST_BYTES;
         if (it >= NS) ptx::mbar_wait(&bar_stfree[s], (k - 1) & 1);
-        const int row0 = img * L;
         ptx::mbar_expect_tx(&bar_qk[s], 128 * 128 + Lk * 128);
+        if (MASK == MASK_BLOCK) {  // two 64-row slots: images 2 * img and 2 * img + 1 (tmap_kv has a 64-row box)
+          const int ra = 2 * img * Lblk, rb = ra + Lblk;
+          ptx::tma_load_2d(st + ST_Q, &tmap_kv, &bar_qk[s], h * 64, ra);
+          ptx::tma_load_2d(st + ST_Q + 8192, &tmap_kv, &bar_qk[s], h * 64, rb);
+          ptx::tma_load_2d(st + ST_K, &tmap_kv, &bar_qk[s], D + h * 64, ra);
+          ptx::tma_load_2d(st + ST_K + 8192, &tmap_kv, &bar_qk[s], D + h * 64, rb);
+          ptx::mbar_expect_tx(&bar_v[s], Lk * 128);
+          ptx::tma_load_2d(st + ST_V, &tmap_kv, &bar_v[s], 2 * D + h * 64, ra);
+          ptx::tma_load_2d(st + ST_V + 8192, &tmap_kv, &bar_v[s], 2 * D + h * 64, rb);
+          continue;
+        }
+        const int row0 = img * L;
         ptx::tma_load_2d(st + ST_Q, &tmap_q, &bar_qk[s], h * 64, row0 + qt * 128);
         ptx::tma_load_2d(st + ST_K, &tmap_kv, &bar_qk[s], D + h * 64, row0);
         ptx::mbar_expect_tx(&bar_v[s], Lk * 128);
@@ -243,14 +256,17 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // O(prev) -> global: this thread owns 32 of the 64 output columns of its row
     auto epilogue = [&](int img, int h, int qt, int b) {
       if (qt * 128 + quad * 32 >= L) return;
-      const int valid = MASK == MASK_BLOCK ? min(L, rows_total - img * L) : L;  // rows of this sequence that exist
       uint32_t o[32];
       ptx::tmem_ld_32x32(tmem + lane_off + TM_O + half * 32, o);
       ptx::tmem_ld_wait();
       const int grow = qt * 128 + row;
-      if (grow < valid) {
+      // MASK_BLOCK: row -> (slot, token); image 2 * img + slot exists if it is below rows_total (= number of images)
+      const int image = MASK == MASK_BLOCK ? 2 * img + (row >> 6) : img;
+      const int tok = MASK == MASK_BLOCK ? (row & 63) : grow;
+      const int seq_len = MASK == MASK_BLOCK ? Lblk : L;
+      if (tok < seq_len && (MASK != MASK_BLOCK || image < rows_total)) {
         const float inv_l = 1.0f / (s_sum[b * 256 + row] + s_sum[b * 256 + 128 + row]);
-        uint16_t* dst = out + (static_cast<size_t>(img) * L + grow) * D + h * 64 + half * 32;
+        uint16_t* dst = out + (static_cast<size_t>(image) * seq_len + tok) * D + h * 64 + half * 32;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint4 v;
@@ -276,8 +292,8 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // valid key columns [lo, lim) of this thread's row
       int lo = 0, lim = L;
       if (MASK == MASK_CAUSAL) lim = min(L, qt * 128 + row + 1);
-      if (MASK == MASK_BLOCK) {
-        lo = min(row / Lblk, L / Lblk - 1) * Lblk;  // tile rows past the sequence reuse the last block (never stored)
+      if (MASK == MASK_BLOCK) {  // the row's own 64-key slot
+        lo = (row >> 6) << 6;
         lim = lo + Lblk;
       }
       softmax_item<BF16, NC, MASK>(t_row, c_begin, lo, lim, sl2, s_max + b * 256, s_sum + b * 256, half, row, has_rows);
@@ -342,23 +358,20 @@ cudaError_t launch_dt(int nc, const CUtensorMap& tq, const CUtensorMap& tkv, uin
 
 }  // namespace
 
-// images packed into one sequence: 1 for L > 64, else as many whole images as fit 128 query rows.
-// OPT-IN (AIHAB_ATTN_PACK=1): where an image's keys fall inside the 16-key MMA steps depends on its position in the
-// pack, so the fp32 accumulation order of O - and with it the last bits of the result - depends on which images share
-// a tile.  The extraction path promises per-image results that are bit-identical for every batch composition and
-// shard count, so the default keeps one image per sequence and L <= 64 on the mma.sync kernel.
+// images per tile: 2 (64-row slots) for 16 <= L <= 64, else 1.  AIHAB_ATTN_PACK=0 sends L <= 64 back to the mma.sync
+// kernel (A/B runs).
 int attention_tcp_pack(int L) {
   static const bool enabled = [] {  // read once: tensor maps built at create and launches must agree
     const char* e = getenv("AIHAB_ATTN_PACK");
-    return e != nullptr && e[0] == '1';
+    return !(e != nullptr && e[0] == '0');
   }();
-  return (L > 64 || !enabled) ? 1 : 128 / L;
+  return (L > 64 || !enabled) ? 1 : 2;
 }
 bool attention_tcp_supported(int L) {
   const int g = attention_tcp_pack(L);
-  return L >= 16 && (L > 64 || g > 1) && (L * g + 15) / 16 * 16 <= KV_MAX;
+  return L >= 16 && (L > 64 || g > 1) && (g > 1 || (L + 15) / 16 * 16 <= KV_MAX);
 }
-int attention_tcp_key_rows(int L) { return (L * attention_tcp_pack(L) + 15) / 16 * 16; }
+int attention_tcp_key_rows(int L) { return attention_tcp_pack(L) > 1 ? 64 : (L + 15) / 16 * 16; }
 
 cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, void* out, int n_img, int L,
                                  int H, int is_bf16, int num_sms, cudaStream_t stream, int reverse, int causal,
@@ -369,7 +382,7 @@ cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& t
   if (g > 1 && causal) return cudaErrorInvalidValue;  // the text tower has L = 77
   if (g == 1 && !causal && tmap_out3 != nullptr && attention_tcd_supported(L))  // two query tiles per unit: dual-stream kernel
     return launch_attention_tcd(tmap_q, tmap_kv, *tmap_out3, n_img, L, H, is_bf16, num_sms, stream, reverse);
-  const int Ls = g * L;                       // rows per sequence
+  const int Ls = g > 1 ? 128 : L;             // rows per tile sequence (two 64-row slots when packed)
   const int n_seq = (n_img + g - 1) / g;
   const int Lk = (Ls + 15) / 16 * 16;
   const int nq = (Ls + 127) / 128;
@@ -377,7 +390,7 @@ cudaError_t launch_attention_tcp(const CUtensorMap& tmap_q, const CUtensorMap& t
   int grid = total < num_sms ? total : num_sms;
   if (nq == 2) grid &= ~1;  // even: a CTA's items alternate between the full and the partial query tile
   const int nc = ((Lk >> 4) + 1) >> 1;
-  const int rows_total = n_img * L;
+  const int rows_total = g > 1 ? n_img : n_img * L;  // packed: the number of images (the last pair may be half empty)
   uint16_t* o = static_cast<uint16_t*>(out);
   if (g > 1)
     return is_bf16 ? launch_dt<true, MASK_BLOCK>(nc, tmap_q, tmap_kv, o, Ls, H, Lk, nq, total, grid, reverse, L, rows_total, stream)
