@@ -88,6 +88,8 @@ int fail(const std::string& msg) {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+cudaMemPool_t temp_pool(int dev);
+
 // Stream-ordered temporary that is returned to the pool on EVERY exit path (the CK macros return early on errors).
 template <typename T>
 struct AsyncTemp {
@@ -96,7 +98,13 @@ struct AsyncTemp {
   explicit AsyncTemp(cudaStream_t stream) : s(stream) {}
   AsyncTemp(const AsyncTemp&) = delete;
   AsyncTemp& operator=(const AsyncTemp&) = delete;
-  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, s); }
+  cudaError_t alloc(size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool = temp_pool(dev);
+    return pool ? cudaMallocFromPoolAsync(reinterpret_cast<void**>(&p), bytes, pool, s)
+                : cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, s);
+  }
   ~AsyncTemp() {
     if (p != nullptr) cudaFreeAsync(p, s);
   }
@@ -140,21 +148,31 @@ int device_of(const void* p) {
   return d;
 }
 
-// Stream-ordered temporaries (aihab_score / aihab_score16) come from the device's default memory pool; keep freed
-// blocks cached in the pool instead of returning them to the driver at every synchronisation point.
-void keep_pool_warm(int dev) {
+// Stream-ordered temporaries (aihab_score / aihab_score16 / aihab_prototype_scores) come from a PRIVATE memory pool per
+// device whose freed blocks stay cached (release threshold = max) - the process-wide default pool is left alone.
+cudaMemPool_t temp_pool(int dev) {
   static std::mutex mu;
-  static std::map<int, bool> done;
+  static std::map<int, cudaMemPool_t> pools;
   std::lock_guard<std::mutex> lk(mu);
-  if (done[dev]) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+  auto it = pools.find(dev);
+  if (it != pools.end()) return it->second;
+  cudaMemPool_t pool = nullptr;
+  cudaMemPoolProps props{};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = dev;
+  if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
     uint64_t threshold = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  } else {
+    cudaGetLastError();
+    pool = nullptr;  // fall back to the default pool (cudaMallocAsync)
   }
-  cudaGetLastError();
-  done[dev] = true;
+  pools[dev] = pool;
+  return pool;
 }
+void keep_pool_warm(int dev) { (void)temp_pool(dev); }
 
 // CTA-pair (tcgen05 cta_group::2) GEMM tiles: AIHAB_GEMM_PAIR=1/0 forces them on/off, default = gemm_use_pair()
 bool gemm_pair_enabled(int M, int N, int sms) {

@@ -305,3 +305,26 @@ def test_engine_lifecycle_and_bf16_warning(tmp_path, cuda_device):
         warnings.simplefilter("always")
         model.encode_image(x)
     assert any("outside the parity" in str(i.message).lower() or "OUTSIDE the parity" in str(i.message) for i in w)
+
+
+def test_sharded_extractor_host_copy_is_complete_on_return(tmp_path, cuda_device):
+    """run() must not hand out `host_copy` while its device->host copies are still in flight, and a second
+    run() must not silently change what the first one returned to a caller who copied it."""
+    from aihab_clip_b200.extraction import ShardedExtractor, ZeroShotHead, array_source
+    geom = GEOMETRIES["ViT-tiny/16"]
+    _, model, _ = load_model(tmp_path, geom.name, 0, cuda_device)
+    model.float()
+    g = torch.Generator().manual_seed(1)
+    tw = torch.nn.functional.normalize(torch.randn(geom.embed_dim, 20, generator=g), dim=0)
+    head = ZeroShotHead.from_model(model, tw, cuda_device)
+    u8 = synthetic_images_u8(37, 64)
+    ext = ShardedExtractor(model, head, batch_size=8, device=cuda_device, rank=0, world_size=1, copy_results_to_host=True)
+    res = ext.run(array_source(u8), 37)
+    host = res["host_copy"][:37].clone()           # read on the CPU immediately, no synchronize in between
+    E = geom.embed_dim
+    assert torch.equal(host[:, :E], res["features"].cpu()) and torch.equal(host[:, E].long(), res["preds"].cpu())
+    assert ext.h2d_bytes == u8.nbytes and ext.d2h_bytes == 37 * (E + 1) * 4
+    assert ext.last_compute_ms > 0
+    res2 = ext.run(array_source(u8[::-1].copy()), 37)
+    assert torch.equal(res2["host_copy"][:37][:, :E], res2["features"].cpu())
+    assert torch.equal(host[:, :E], res["features"].cpu())   # the clone taken after run() 1 is unaffected
