@@ -1108,7 +1108,23 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
   CK(w3_t.alloc(static_cast<size_t>(C) * 3 * E * 2));
   CK(a3_t.alloc(static_cast<size_t>(rows_tmp) * 3 * E * 2));
   CK(emb_raw_t.alloc(static_cast<size_t>(rows_tmp) * E * 4));
-  if (logits_out == nullptr) CK(logit_t.alloc(static_cast<size_t>(rows_tmp) * C * 4));
+  // k <= 8 and no logits requested: the logits GEMM keeps per-row top-k candidates in its epilogue (EPI_TOPK_32) and the
+  // [rows, C] logits never reach HBM; AIHAB_SCORE16_FUSED=0 restores the store + top-k kernel pair (A/B, tests)
+  static const bool fused_env = [] {
+    const char* e = getenv("AIHAB_SCORE16_FUSED");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool fused = fused_env && logits_out == nullptr && k > 0 && k <= aihab::TOPK_SLOTS;
+  const int bn_logits = aihab::gemm_block_n(rows_tmp, C, sms);
+  const int cand_slots = 2 * ((C + bn_logits - 1) / bn_logits);
+  AsyncTemp<float> cand_val_t(s);
+  AsyncTemp<int> cand_idx_t(s);
+  if (fused) {
+    CK(cand_val_t.alloc(static_cast<size_t>(rows_tmp) * cand_slots * aihab::TOPK_SLOTS * 4));
+    CK(cand_idx_t.alloc(static_cast<size_t>(rows_tmp) * cand_slots * aihab::TOPK_SLOTS * 4));
+  } else if (logits_out == nullptr) {
+    CK(logit_t.alloc(static_cast<size_t>(rows_tmp) * C * 4));
+  }
   void *projT = projT_t.p, *w3 = w3_t.p, *a3 = a3_t.p;
   float *emb_raw = emb_raw_t.p, *logit_tmp = logit_t.p;
   ProfScope ps(PC_SCORE, 2.0 * n * (static_cast<double>(D) * E + static_cast<double>(E) * C), s);
@@ -1136,15 +1152,25 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
     CKL(aihab::launch_l2norm_split(emb_raw, emb_out ? emb_out + static_cast<size_t>(i0) * E : nullptr, a3, nb, E, s));
     // logits = scale * (e_hi w_hi + e_hi w_lo + e_lo w_hi): one K = 3E fp16 GEMM (methods/utils.py:185)
     float* lg = logits_out ? logits_out + static_cast<size_t>(i0) * C : logit_tmp;
-    bn = aihab::gemm_block_n(nb, C, sms);
+    bn = fused ? bn_logits : aihab::gemm_block_n(nb, C, sms);
     CK(aihab::make_tmap_2d_16bit(&ma, a3, nb, 3 * E, static_cast<uint64_t>(3 * E) * 2, 128, 0));
     CK(aihab::make_tmap_2d_16bit(&mw, w3, C, 3 * E, static_cast<uint64_t>(3 * E) * 2, bn, 0));
     p.N = C;
     p.K = 3 * E;
     p.ab_format = 0;
-    p.out32 = lg;
+    p.out32 = fused ? nullptr : lg;
     p.ldo = C;
     p.scale = scale;
+    if (fused) {
+      p.epilogue = aihab::EPI_TOPK_32;
+      p.cand_val = cand_val_t.p;
+      p.cand_idx = cand_idx_t.p;
+      CKL(aihab::launch_gemm(ma, mw, nullptr, p, bn, sms, s));
+      CKL(aihab::launch_topk_merge(cand_val_t.p, cand_idx_t.p, nb, cand_slots, k, topk_idx + static_cast<size_t>(i0) * k,
+                                   topk_val ? topk_val + static_cast<size_t>(i0) * k : nullptr, s));
+      p.epilogue = aihab::EPI_SCALE_32;  // GEMM 1 of the next pass
+      continue;
+    }
     CKL(aihab::launch_gemm(ma, mw, nullptr, p, bn, sms, s));
     if (k > 0)
       CKL(aihab::launch_topk(lg, nb, C, k, topk_idx + static_cast<size_t>(i0) * k,

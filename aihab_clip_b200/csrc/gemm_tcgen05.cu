@@ -494,6 +494,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tok_row[i] = img * (p.g2 + 1) + pos_row[i];
           }
         }
+        if constexpr (EPI == EPI_TOPK_32) {
+          // running top-TOPK_SLOTS of this thread's accumulator row over the warp's chunks of the tile; columns arrive
+          // in ascending order, so a strict '>' keeps the lower column ahead among equal values (torch.topk order)
+          float tv[TOPK_SLOTS];
+          int ti[TOPK_SLOTS];
+#pragma unroll
+          for (int i = 0; i < TOPK_SLOTS; ++i) {
+            tv[i] = -INFINITY;
+            ti[i] = 0x7fffffff;
+          }
+#pragma unroll 1
+          for (int c = ehalf; c < BN / 32; c += 2) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(taddr + c * 32, r);
+            ptx::tmem_ld_wait();
+            const int col0 = n0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = fmaf(__uint_as_float(r[j]), p.scale, sb[c * 32 + j]);
+              if (col0 + j < p.N && v > tv[TOPK_SLOTS - 1]) {
+                tv[TOPK_SLOTS - 1] = v;
+                ti[TOPK_SLOTS - 1] = col0 + j;
+#pragma unroll
+                for (int i = TOPK_SLOTS - 1; i > 0; --i) {
+                  if (tv[i] > tv[i - 1]) {
+                    const float fv = tv[i];
+                    tv[i] = tv[i - 1];
+                    tv[i - 1] = fv;
+                    const int iv = ti[i];
+                    ti[i] = ti[i - 1];
+                    ti[i - 1] = iv;
+                  }
+                }
+              }
+            }
+          }
+          const int grow = m0 + lane;
+          if (grow < p.M) {
+            const size_t base = (static_cast<size_t>(grow) * (2 * n_blocks) + 2 * (n0 / BN) + ehalf) * TOPK_SLOTS;
+#pragma unroll
+            for (int i = 0; i < TOPK_SLOTS; i += 4) {
+              *reinterpret_cast<float4*>(p.cand_val + base + i) = make_float4(tv[i], tv[i + 1], tv[i + 2], tv[i + 3]);
+              *reinterpret_cast<int4*>(p.cand_idx + base + i) = make_int4(ti[i], ti[i + 1], ti[i + 2], ti[i + 3]);
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int c = ehalf; c < BN / 32; c += 2) {  // 32-column chunks dealt alternately to the quadrant's two warps
           uint32_t r[32];
@@ -549,6 +595,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
           }
           __syncwarp();
+        }
         }
       }
       // accumulator stage drained: hand it back to the MMA issuer (the 16-bit epilogues did so after their last load)
@@ -610,6 +657,7 @@ cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, const CUtens
     case EPI_SCALE_32: return launch_one<BN, EPI_SCALE_32>(ta, tw, tc, p, grid, pair, stream);
     case EPI_LN_BIAS_16: return launch_one<BN, EPI_LN_BIAS_16>(ta, tw, tc, p, grid, pair, stream);
     case EPI_LN_BIAS_GELU_16: return launch_one<BN, EPI_LN_BIAS_GELU_16>(ta, tw, tc, p, grid, pair, stream);
+    case EPI_TOPK_32: return launch_one<BN, EPI_TOPK_32>(ta, tw, tc, p, grid, pair, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -632,7 +680,7 @@ cudaError_t gemm_init() {
   AIHAB_SET(256, EPI_PATCH_32) AIHAB_SET(256, EPI_SCALE_32) AIHAB_SET(256, EPI_LN_BIAS_16)
   AIHAB_SET(256, EPI_LN_BIAS_GELU_16) AIHAB_SET(128, EPI_LN_BIAS_16) AIHAB_SET(128, EPI_LN_BIAS_GELU_16)
   AIHAB_SET(128, EPI_BIAS_16) AIHAB_SET(128, EPI_BIAS_GELU_16) AIHAB_SET(128, EPI_BIAS_RES_32)
-  AIHAB_SET(128, EPI_PATCH_32) AIHAB_SET(128, EPI_SCALE_32)
+  AIHAB_SET(128, EPI_PATCH_32) AIHAB_SET(128, EPI_SCALE_32) AIHAB_SET(256, EPI_TOPK_32) AIHAB_SET(128, EPI_TOPK_32)
 #undef AIHAB_SET
   return cudaSuccess;
 }
@@ -723,7 +771,9 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, co
   if (p.epilogue == EPI_BIAS_RES_32 && p.ln_gamma != nullptr && (p.a16_out == nullptr || p.stats_out == nullptr))
     return cudaErrorInvalidValue;
   if (out16 && ((p.N & 7) || (p.ldo & 7) || p.out16 == nullptr)) return cudaErrorInvalidValue;
-  if (!out16 && ((p.N & 3) || (p.ldo & 3) || p.out32 == nullptr)) return cudaErrorInvalidValue;
+  const bool topk = p.epilogue == EPI_TOPK_32;
+  if (topk && (p.cand_val == nullptr || p.cand_idx == nullptr)) return cudaErrorInvalidValue;
+  if (!out16 && !topk && ((p.N & 3) || (p.ldo & 3) || p.out32 == nullptr)) return cudaErrorInvalidValue;
   if (p.epilogue == EPI_PATCH_32 && (p.pos == nullptr || p.g2 <= 0)) return cudaErrorInvalidValue;
   if (p.epilogue == EPI_BIAS_RES_32 && (tmap_c == nullptr || (p.N & 31))) return cudaErrorInvalidValue;
   CUtensorMap out_map;

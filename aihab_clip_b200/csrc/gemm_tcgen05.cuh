@@ -35,7 +35,13 @@ enum GemmEpilogue : int {
   // with the row statistics (mu, r = rsqrt(var + 1e-5)) rebuilt from the partial sums the producer GEMM stored.
   EPI_LN_BIAS_16 = 5,       // ln_1 -> in_proj                                  clip/model.py:181,184
   EPI_LN_BIAS_GELU_16 = 6,  // ln_2 -> c_fc -> QuickGELU                        clip/model.py:172,185
+  // scale * acc (+ bias) is NOT stored: every epilogue warp keeps, per accumulator row, the TOPK_SLOTS best of the
+  // columns it sees (value descending, lower column first among equals = torch.topk order) and writes them to
+  // cand_val / cand_idx [M, 2 * n_tiles, TOPK_SLOTS]; a merge pass picks the row's final top-k.  The logits of the
+  // scoring path never reach HBM (methods/utils.py:16-21,185-186).
+  EPI_TOPK_32 = 7,
 };
+constexpr int TOPK_SLOTS = 8;  // candidates kept per (row, epilogue warp) in EPI_TOPK_32; k <= TOPK_SLOTS
 
 struct GemmParams {
   int M, N, K;
@@ -61,6 +67,9 @@ struct GemmParams {
   const float* ln_stats;
   int ln_nsb;
   const float* ln_s;
+  // EPI_TOPK_32: candidate buffers [M, 2 * ceil(N / BN), TOPK_SLOTS]
+  float* cand_val;
+  int* cand_idx;
 };
 
 // Encodes a 2-D tiled tensor map over a row-major [rows, cols] 16-bit matrix with a {64, box_rows} box and

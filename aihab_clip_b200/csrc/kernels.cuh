@@ -120,6 +120,10 @@ cudaError_t launch_l2norm_rows(const void* x, int in_dtype, void* y, int out_dty
 cudaError_t launch_topk(const float* logits, int rows, int cols, int k, int64_t* idx, float* val,
                         cudaStream_t stream);
 
+// final top-k over the per-row candidates of the EPI_TOPK_32 GEMM epilogue ([rows, slots, 8] values / int32 columns)
+cudaError_t launch_topk_merge(const float* cand_val, const int* cand_idx, int rows, int slots, int k, int64_t* idx,
+                              float* val, cudaStream_t stream);
+
 // One-launch small-batch scoring (n <= 8192): proj -> normalise -> logits -> top-k; bit-identical to the chain above.
 bool score_fused_supported(int n, int D, int E, int C);
 cudaError_t launch_score_fused(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C,

@@ -168,6 +168,35 @@ __global__ void __launch_bounds__(128) topk_regs_kernel(const float* __restrict_
   }
 }
 
+// Final selection over the candidates the EPI_TOPK_32 GEMM epilogue left per row: [rows, slots, 8] values and column
+// indices (unused entries are -inf / INT_MAX).  One thread per row, k rounds in (value desc, index asc) order.
+__global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
+                                                         int rows, int slots, int k, int64_t* __restrict__ idx,
+                                                         float* __restrict__ val) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const float4* cv = reinterpret_cast<const float4*>(cand_val + static_cast<size_t>(row) * slots * 8);
+  const int4* ci = reinterpret_cast<const int4*>(cand_idx + static_cast<size_t>(row) * slots * 8);
+  float last_v = INFINITY;
+  int last_i = -1;
+  for (int j = 0; j < k; ++j) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int q = 0; q < slots * 2; ++q) {
+      const float4 v = __ldg(cv + q);
+      const int4 c = __ldg(ci + q);
+      if (precedes(last_v, last_i, v.x, c.x) && precedes(v.x, c.x, bv, bi)) { bv = v.x; bi = c.x; }
+      if (precedes(last_v, last_i, v.y, c.y) && precedes(v.y, c.y, bv, bi)) { bv = v.y; bi = c.y; }
+      if (precedes(last_v, last_i, v.z, c.z) && precedes(v.z, c.z, bv, bi)) { bv = v.z; bi = c.z; }
+      if (precedes(last_v, last_i, v.w, c.w) && precedes(v.w, c.w, bv, bi)) { bv = v.w; bi = c.w; }
+    }
+    idx[static_cast<size_t>(row) * k + j] = bi;
+    if (val != nullptr) val[static_cast<size_t>(row) * k + j] = bv;
+    last_v = bv;
+    last_i = bi;
+  }
+}
+
 // Small-batch path (one extraction batch): proj -> L2 normalise -> scaled logits -> top-k in ONE launch.
 // RPB rows per CTA share every visual.proj / text-weight element they load.  Thread layout for the projection:
 // 128 column quads (float4 loads of one contiguous proj row per k) x 2 halves of K, 8 loads in flight per thread;
@@ -746,6 +775,14 @@ cudaError_t launch_topk(const float* logits, int rows, int cols, int k, int64_t*
     topk_regs_kernel<8><<<(rows + 3) / 4, 128, 0, stream>>>(logits, rows, cols, k, idx, val);
   else
     topk_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(logits, rows, cols, k, idx, val);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_topk_merge(const float* cand_val, const int* cand_idx, int rows, int slots, int k, int64_t* idx,
+                              float* val, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (k <= 0 || k > 8 || slots <= 0) return cudaErrorInvalidValue;
+  topk_merge_kernel<<<(rows + 127) / 128, 128, 0, stream>>>(cand_val, cand_idx, rows, slots, k, idx, val);
   return cudaGetLastError();
 }
 

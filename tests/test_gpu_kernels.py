@@ -343,3 +343,25 @@ def test_prototype_scores_match_reference_golden(cuda_device):
     o1 = ops.prototype_scores(torch.from_numpy(emb[:100]).to(cuda_device), torch.full((100,), int(owner[0]), device=cuda_device),
                               torch.from_numpy(protos[one]).to(cuda_device), torch.from_numpy(owner[one]).to(cuda_device))
     assert torch.isnan(o1[2]).all() and torch.isnan(o1[3]).all()
+
+
+def test_score16_fused_topk_equals_the_unfused_path(cuda_device):
+    """EPI_TOPK_32: the logits GEMM keeps per-row top-k candidates in its epilogue and a merge pass finishes the selection,
+    so the [rows, C] logits never reach HBM.  Same GEMM arithmetic, same (value desc, index asc) order: indices and
+    values must equal those of the store + top-k kernel pair (requesting the logits selects that path) bit for bit,
+    including exact ties and rows spanning several passes."""
+    _lib, ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for (n, D, E, Cn, k) in ((40000, 768, 512, 1000, 5), (777, 128, 64, 20, 3), (3000, 256, 128, 260, 8)):
+        feats = torch.randn(n, D, generator=g).half().to(cuda_device)
+        proj = (torch.randn(D, E, generator=g) * D ** -0.5).half().to(cuda_device)
+        tw = torch.nn.functional.normalize(torch.randn(Cn, E, generator=g), dim=1).t().contiguous()
+        tw[:, 7] = tw[:, 3]                                    # two identical classes: exact ties in every row
+        tw = tw.to(cuda_device)
+        _, _, idx_f, val_f = ops.score16(feats, proj, tw, 100.0, k)                      # fused (no logits requested)
+        _, logits, idx_u, val_u = ops.score16(feats, proj, tw, 100.0, k, want_logits=True)  # logits stored + top-k kernel
+        assert torch.equal(idx_f, idx_u) and torch.equal(val_f, val_u)
+        ref = logits.topk(k, 1, True, True)
+        assert torch.equal(val_f, ref.values)
+        both = (idx_f == 3) | (idx_f == 7)
+        assert both.any() and (idx_f[both.any(dim=1)].eq(3).any(dim=1)).all()   # tie: the lower index is always present first
