@@ -53,9 +53,23 @@ extern "C" __attribute__((visibility("default"))) int aihab_debug_attn_timing(lo
 #define AIHAB_ATTN_EXPERIMENT 0
 #endif
 
+// waits of the softmax / issuer warps: -DAIHAB_TCD_BACKOFF=<ns> sleeps between polls (experiment: do polling warps take
+// issue slots from the working warp of their scheduler?)
+#ifndef AIHAB_TCD_BACKOFF
+#define AIHAB_TCD_BACKOFF 0
+#endif
+
 namespace aihab {
 
 namespace {
+
+__device__ __forceinline__ void tcd_wait(uint64_t* bar, uint32_t parity) {
+#if AIHAB_TCD_BACKOFF > 0
+  ptx::mbar_wait_backoff(bar, parity, AIHAB_TCD_BACKOFF);
+#else
+  ptx::mbar_wait(bar, parity);
+#endif
+}
 
 __device__ __forceinline__ float exp2_poly(float x) {
   x = fmaxf(x, -125.0f);
@@ -184,9 +198,9 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     for (int u = 0; u < n_units; ++u) {
       const int s = u % NSTG, ks = u / NSTG;
       TSTAMP(g, 0);
-      ptx::mbar_wait(&bar_qk[s], ks & 1);
+      tcd_wait(&bar_qk[s], ks & 1);
       TSTAMP(g, 1);
-      if (u > 0) ptx::mbar_wait(&bar_bfree[g], (u - 1) & 1);  // O(u-1) has been read out of this buffer
+      if (u > 0) tcd_wait(&bar_bfree[g], (u - 1) & 1);  // O(u-1) has been read out of this buffer
       ptx::tc_fence_after();
       TSTAMP(g, 2);
       const uint32_t st = ptx::smem_u32(smem + s * ST_BYTES);
@@ -204,17 +218,17 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int k_early = early ? 2 * P_SPLIT : 0;
       const uint32_t t_o = tbuf + o_col(early);
       if (k_early) {
-        ptx::mbar_wait(&bar_p1[g], u & 1);
-        ptx::mbar_wait(&bar_v[s], ks & 1);
+        tcd_wait(&bar_p1[g], u & 1);
+        tcd_wait(&bar_v[s], ks & 1);
         ptx::tc_fence_after();
         for (int j = 0; j < k_early; ++j) {
           const uint64_t vd = ptx::make_mnmajor_sw128_desc(v_base + j * 2048);
           ptx::umma_f16_ts_w(t_o, tbuf + p_col(early, j >> 1) + (j & 1) * 8, vd, idesc_o, j != 0);  // A = P from TMEM
         }
       }
-      ptx::mbar_wait(&bar_p[g], u & 1);
+      tcd_wait(&bar_p[g], u & 1);
       TSTAMP(g, 4);
-      ptx::mbar_wait(&bar_v[s], ks & 1);
+      tcd_wait(&bar_v[s], ks & 1);
       ptx::tc_fence_after();
       for (int j = k_early; j < ksteps; ++j) {
         const uint64_t vd = ptx::make_mnmajor_sw128_desc(v_base + j * 2048);
@@ -239,7 +253,7 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       int img, h;
       decode(u, img, h);
       if (quad == 0) TSTAMP(2 + g, 0);
-      ptx::mbar_wait(&bar_sfull[g], u & 1);
+      tcd_wait(&bar_sfull[g], u & 1);
       ptx::tc_fence_after();
       if (quad == 0) TSTAMP(2 + g, 1);
       float l = 0.f;
@@ -288,7 +302,7 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // ---- pass 2: P = exp2(S * scale - max) packed over the S columns, row sum in the thread.  The exp2 phase is
         // MUFU-bound: the two streams' warps of this scheduler take turns in it
         if (quad == 0) TSTAMP(2 + g, 2);
-        if (!(AIHAB_ATTN_EXPERIMENT & 8)) ptx::mbar_wait(&bar_turn[g * 4 + quad], (u & 1) ^ (g == 0 ? 1 : 0));
+        if (!(AIHAB_ATTN_EXPERIMENT & 8)) tcd_wait(&bar_turn[g * 4 + quad], (u & 1) ^ (g == 0 ? 1 : 0));
         if (quad == 0) TSTAMP(2 + g, 3);
         float l0 = 0.f, l1 = 0.f;
         float l2 = 0.f, l3 = 0.f;
@@ -366,7 +380,7 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (quad == 0) TSTAMP(2 + g, 5);
       } else {  // a quadrant without rows (second tile, rows >= L) only passes the token on
         if (early && lane == 0) ptx::mbar_arrive(&bar_p1[g]);
-        if (!(AIHAB_ATTN_EXPERIMENT & 8)) ptx::mbar_wait(&bar_turn[g * 4 + quad], (u & 1) ^ (g == 0 ? 1 : 0));
+        if (!(AIHAB_ATTN_EXPERIMENT & 8)) tcd_wait(&bar_turn[g * 4 + quad], (u & 1) ^ (g == 0 ? 1 : 0));
         if (lane == 0) ptx::mbar_arrive(&bar_turn[(g ^ 1) * 4 + quad]);
       }
       ptx::tc_fence_before();  // P stored (wait::st) before the PV MMA may read it
@@ -374,7 +388,7 @@ attention_tcd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (lane == 0) ptx::mbar_arrive(&bar_p[g]);
 
       if (quad == 0) TSTAMP(2 + g, 6);
-      ptx::mbar_wait(&bar_o[g], u & 1);
+      tcd_wait(&bar_o[g], u & 1);
       ptx::tc_fence_after();
       if (quad == 0) TSTAMP(2 + g, 7);
       uint32_t (&o)[64] = reinterpret_cast<uint32_t(&)[64]>(buf[0]);
