@@ -111,7 +111,8 @@ def test_layernorm(cuda_device, D, out_dtype):
                                    (256, 4, 2), (100, 2, 3), (129, 2, 2), (65, 1, 5), (197, 12, 9), (225, 2, 3),
                                    (272, 3, 5), (273, 2, 2), (384, 2, 2), (600, 1, 2), (1024, 1, 1), (257, 16, 40),
                                    (80, 1, 2), (96, 1, 2), (160, 2, 2), (176, 1, 3), (192, 2, 2), (208, 1, 2),
-                                   (50, 12, 5), (16, 1, 9), (33, 2, 7), (64, 2, 3), (43, 1, 2), (50, 2, 301), (24, 3, 11)])
+                                   (50, 12, 5), (16, 1, 9), (33, 2, 7), (64, 2, 3), (43, 1, 2), (50, 2, 301), (24, 3, 11),
+                                   (224, 2, 3), (210, 3, 2), (144, 1, 5), (130, 2, 1)])
 def test_attention(cuda_device, dtype, L, H, n):
     _lib, ops = _ops()
     rng = np.random.default_rng(L + H)
