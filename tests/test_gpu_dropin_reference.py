@@ -79,3 +79,27 @@ def test_reference_callers_run_on_our_model(tmp_path, cuda_device, reference_mod
     x16, _ = R["mu"].compute_image_features(model16, CC.case_loader(tf, False), to_cpu=False)
     assert x16.dtype == torch.float16 and x16.is_cuda
     np.testing.assert_allclose(x16.float().cpu().numpy(), ref_gold["pre_f0"], atol=2e-2, rtol=0)
+
+
+def test_reference_pre_load_features_and_cache_model_on_our_model(tmp_path, cuda_device, reference_modules):
+    """utils.pre_load_features (utils.py:60-82) and methods.utils.build_cache_model (methods/utils.py:31-45) — the
+    reference's own code, which moves batches with `.cuda()` and normalises with torch — on the model our clip.load
+    returns, against what they produce on the reference's model."""
+    R = reference_modules
+    ref_gold = np.load(GOLDEN / "reference_cache.npz")
+    ref_meta = json.loads((GOLDEN / "reference_cache.json").read_text())
+    import aihab_clip_b200.clip as clip
+    path = tmp_path / "tiny16.pt"
+    torch.save(make_state_dict("ViT-tiny/16", 0), path)
+    state, model, _ = clip.load(str(path), device=cuda_device, jit=False)
+    model.float()
+    tf = R["tf"]({}, is_train=False, resolution=64)
+    f, l = R["u"].pre_load_features({"load_pre_feat": False, "cache_dir": str(tmp_path)}, "val", model, CC.case_loader(tf, False))
+    assert sorted(p.name for p in tmp_path.glob("val_*.pt")) == ref_meta["preload_files"]
+    np.testing.assert_allclose(f.cpu().numpy(), ref_gold["preload_f"], atol=2e-3, rtol=0)
+    np.testing.assert_array_equal(l.cpu().numpy(), ref_gold["preload_l"])
+    proj = state["visual.proj"].float()
+    keys, values = R["mu"].build_cache_model({"load_cache": False, "augment_epoch": 2, "cache_dir": str(tmp_path / "tip")},
+                                             model, CC.case_loader(tf, False), 0, lambda x: x @ proj)
+    np.testing.assert_allclose(keys.float().cpu().numpy(), ref_gold["tip_keys"], atol=2e-3, rtol=0)
+    np.testing.assert_array_equal(values.float().cpu().numpy(), ref_gold["tip_values"])

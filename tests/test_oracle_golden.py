@@ -206,3 +206,24 @@ def test_headline_geometry_is_pinned_to_the_reference(gold_vitl):
     _, logits_t, _ = OT.score(OT.encode_image(sdt, OT.preprocess_pil(u8, geom.image_resolution)), sdt["visual.proj"],
                               torch.from_numpy(tw), 100.0, 3)
     np.testing.assert_allclose(logits_t.numpy(), gold_vitl["b16_logits"], atol=5e-4, rtol=0)
+
+
+def test_full_depth_goldens_pin_the_torch_restatement(gold, gold_full):
+    """The full-depth fixtures of tests/golden/make_golden_full.py (unmodified reference, CPU fp32): the torch-operator
+    restatement reproduces the reference's ViT-L/14 features for the first two images of the config-3 set (24 blocks,
+    width 1024) and the config-1 logits (ViT-B/32, 18 x 80 head) for the first eight images."""
+    import torch
+    from oracle import clip_oracle_torch as OT
+    geom = GEOMETRIES["ViT-L/14"]
+    sdt = OT.to_torch_state(make_state_dict_np(geom, 0, with_text=False))
+    u8 = np.concatenate([synthetic_images_u8(4, 300, seed=1234), synthetic_images_u8(4, 300, seed=1234, start=4, smooth=True)])
+    x = OT.preprocess_pil(u8, 224)
+    assert sha(x.numpy()) == gold_full["l14_pre_sha"].tobytes(), "preprocessing must be bit-exact"
+    feats = OT.encode_image(sdt, x[:2])
+    np.testing.assert_allclose(feats.numpy(), gold_full["l14_feats"][:2], atol=5e-4, rtol=0)
+    geom = GEOMETRIES["ViT-B/32"]
+    sdt = OT.to_torch_state(make_state_dict_np(geom, 0, with_text=False))
+    u8 = np.concatenate([synthetic_images_u8(32, 224, seed=4321), synthetic_images_u8(32, 224, seed=4321, start=32, smooth=True)])
+    _, logits, top3 = OT.score(OT.encode_image(sdt, OT.preprocess_pil(u8[:8], 224)), sdt["visual.proj"],
+                               torch.from_numpy(gold["b32_text_w_18x80"]), 100.0, 3)
+    np.testing.assert_allclose(logits.numpy(), gold_full["c1_logits"][:8], atol=5e-4, rtol=0)
