@@ -371,6 +371,12 @@ struct aihab_vit {
   // concurrently with the tensor-core kernel, fork / join through the two events
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // pipelined MLP (AIHAB_MLP_PIPE=1): c_fc and c_proj run concurrently on half of the SMs each, the hidden activations
+  // pass through an L2-resident ring in the front of `big`
+  bool mlp_pipe = false;
+  int ring_rows = 0;
+  unsigned* mlp_ctr = nullptr;   // [2][cap_rows / 256] progress counters (done | consumed)
+  CUtensorMap m_hring;           // A operand of c_proj over the ring
   size_t ws_bytes = 0;
   std::vector<void*> allocs;
 };
@@ -548,6 +554,61 @@ int run_blocks(aihab_vit* h, int n, cudaStream_t s) {
         return 1;
     }
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))   (clip/model.py:171-175,185)
+    if (h->mlp_pipe && h->ln_fold && (M % 256) == 0 && M / 256 > h->ring_rows / 256 && h->num_sms >= 4) {
+      // Pipelined pair: c_fc (stream s) and c_proj (side stream) run CONCURRENTLY, each on half of the SMs; c_fc's
+      // 16-bit hidden rows go through a ring of h->ring_rows rows that stays in L2 (per-pair-row progress counters in
+      // global memory order the two kernels), so the [M, 4D] hidden activations never make the HBM round trip.
+      const int pairs = M / 256, half = (h->num_sms / 4) * 2;  // SMs per kernel (an even number: CTA pairs)
+      unsigned* ctr_done = h->mlp_ctr;
+      unsigned* ctr_cons = h->mlp_ctr + h->cap_rows / 256 + 1;
+      CK(cudaMemsetAsync(h->mlp_ctr, 0, 2 * (h->cap_rows / 256 + 1) * sizeof(unsigned), s));
+      ProfScope ps(PC_GEMM, 2.0 * M * (4.0 * D) * D * 2.0, s, -4 * D);  // both GEMMs as one site (they overlap)
+      CK(cudaEventRecord(h->ev_fork, s));
+      CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      aihab::GemmParams p{};
+      p.M = M;
+      p.ab_format = h->bf16;
+      p.scale = 1.0f;
+      p.ring_rows = h->ring_rows;
+      p.ctr_done = ctr_done;
+      p.ctr_consumed = ctr_cons;
+      p.need_done = static_cast<unsigned>((4 * D / 256) * 2 * 8);  // n tiles x 2 CTAs x 8 epilogue warps
+      p.need_consumed = static_cast<unsigned>((D / 256) * 2);       // n tiles x 2 CTAs
+      {  // producer: c_fc (LN fold + bias + QuickGELU) -> ring
+        aihab::GemmParams a = p;
+        a.ring_mode = 1;
+        a.N = 4 * D;
+        a.K = D;
+        a.epilogue = aihab::EPI_LN_BIAS_GELU_16;
+        a.bias = b.bp_fc;
+        a.out16 = h->big;
+        a.ldo = 4 * D;
+        a.ln_stats = h->ln_stats;
+        a.ln_nsb = nsb;
+        a.ln_s = b.s_fc;
+        CKL(aihab::launch_gemm(h->m_y2, b.m_fc[0], nullptr, a, 256, half, s, true));
+      }
+      {  // consumer: c_proj (+ fp32 residual, LayerNorm producer for the next block) <- ring
+        aihab::GemmParams c = p;
+        c.ring_mode = 2;
+        c.N = D;
+        c.K = 4 * D;
+        c.epilogue = aihab::EPI_BIAS_RES_32;
+        c.bias = b.b_proj;
+        c.out32 = h->x;
+        c.ldo = D;
+        if (l + 1 < layers) {
+          c.ln_gamma = h->blocks[l + 1].ln1_g;
+          c.a16_out = h->y2;
+          c.stats_out = h->ln_stats;
+        }
+        CKL(aihab::launch_gemm(h->m_hring, b.m_proj[0], &h->m_x, c, 256, half, h->side, true));
+      }
+      nsb = (D + 127) / 128;
+      CK(cudaEventRecord(h->ev_join, h->side));
+      CK(cudaStreamWaitEvent(s, h->ev_join, 0));
+      continue;
+    }
     if (!h->ln_fold) {
       {
         ProfScope ps(PC_LN, 6.0 * M * D, s);
@@ -654,6 +715,29 @@ int build_stack(aihab_vit* h, int layers, const aihab_vit_block_weights* blocks,
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
       fail("aihab_vit_create: could not create the attention side stream");
       return 1;
+    }
+  }
+  {
+    const char* e = getenv("AIHAB_MLP_PIPE");
+    const int ring = 8192;  // rows: 32 pair-rows x 4D x 2 B = 50 MB at D = 768
+    if (e != nullptr && e[0] == '1' && h->ln_fold && (D % 256) == 0 && h->cap_rows > static_cast<size_t>(2 * ring)) {
+      if (dev_alloc(h, reinterpret_cast<void**>(&h->mlp_ctr), 2 * (h->cap_rows / 256 + 1) * sizeof(unsigned))) return 1;
+      if (aihab::make_tmap_2d_16bit(&h->m_hring, h->big, ring, 4 * D, static_cast<uint64_t>(4 * D) * 2, 128, h->bf16) !=
+          cudaSuccess) {
+        fail("aihab_vit_create: cuTensorMapEncodeTiled failed for the MLP ring view");
+        return 1;
+      }
+      if (h->side == nullptr && cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) {
+        fail("aihab_vit_create: could not create the side stream");
+        return 1;
+      }
+      if (h->ev_fork == nullptr && (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                                    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+        fail("aihab_vit_create: could not create the fork / join events");
+        return 1;
+      }
+      h->ring_rows = ring;
+      h->mlp_pipe = true;
     }
   }
   if (h->attn_kind > 0) {

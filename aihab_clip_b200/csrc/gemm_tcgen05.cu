@@ -165,12 +165,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int tile = unit; tile < num_tiles; tile += num_units) {
         const int m_blk = tile_m(tile);
         const int n_blk = tile % n_blocks;
+        int a_row = m_blk * BM;
+        if constexpr (TWO) {
+          if (p.ring_mode == 2) {  // consumer of a pipelined pair: the producer kernel has finished this pair-row
+            ptx::wait_counter(p.ctr_done + tile / n_blocks, p.need_done);
+            ptx::fence_proxy_async_all();  // its TMA stores (async proxy, other SMs) before our TMA loads
+            a_row %= p.ring_rows;
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           if constexpr (TWO) {
             // both CTAs' loads complete on the leader's barrier: it expects the bytes of the whole pair
             if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-            ptx::tma_load_2d_pair(sA + stage * L::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM, pol_a);
+            ptx::tma_load_2d_pair(sA + stage * L::kABytes, &tmap_a, &full_bar[stage], kb * BK, a_row, pol_a);
             ptx::tma_load_2d_pair(sB + stage * L::kBBytes, &tmap_w, &full_bar[stage], kb * BK,
                                   n_blk * BN + cta_rank * (BN / 2), pol_w);
             if (++stage == kStages) {
@@ -340,6 +348,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
+      if constexpr (TWO && EPI == EPI_BIAS_RES_32) {
+        // consumer of a pipelined pair: every MMA of the tile has retired, so this CTA's A rows of the ring are consumed
+        if (p.ring_mode == 2 && warp == EPI_WARP0 && lane == 0) ptx::red_release_gpu_add(p.ctr_consumed + tile / n_blocks, 1u);
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       if (kOut16 && p.debug == 77) {  // DEBUG: drain without an epilogue (mainloop ceiling measurement)
         ptx::tc_fence_before();
@@ -351,6 +363,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         continue;
       }
 
+      int st_row = m0;
+      if constexpr (kOut16 && TWO) {
+        if (p.ring_mode == 1) {  // producer of a pipelined pair: the ring slot of this pair-row must have been consumed
+          const int pr = tile / n_blocks, ring_pairs = p.ring_rows / (2 * BM);
+          if (pr >= ring_pairs && lane == 0) ptx::wait_counter(p.ctr_consumed + pr - ring_pairs, p.need_consumed);
+          __syncwarp();
+          st_row = m0 % p.ring_rows;
+        }
+      }
       if constexpr (kOut16) {
         // 64-column chunks, dealt alternately to the two warps of a lane quadrant.  A chunk leaves as ONE TMA store of
         // a 32-row x 128-byte box: the staging tile is written in the SWIZZLE_128B pattern (16-byte units XOR row & 7,
@@ -400,8 +421,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_store_2d(&tmap_c, stg, n0 + c * 64, m0);
+            ptx::tma_store_2d(&tmap_c, stg, n0 + c * 64, st_row);
             ptx::bulk_commit();
+          }
+        }
+        if constexpr (TWO) {
+          if (p.ring_mode == 1 && lane == 0) {  // this warp's share of the tile is in global memory: count it
+            ptx::bulk_wait_all();
+            ptx::fence_proxy_async_all();
+            ptx::red_release_gpu_add(p.ctr_done + tile / n_blocks, 1u);
           }
         }
       } else if constexpr (EPI == EPI_BIAS_RES_32) {
@@ -765,6 +793,11 @@ bool gemm_use_pair(int M, int N, int num_sms) {
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, const CUtensorMap* tmap_c,
                         const GemmParams& p, int block_n, int num_sms, cudaStream_t stream, bool pair) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaErrorInvalidValue;
+  if (p.ring_mode != 0) {  // pipelined pair: CTA pairs, whole pair-rows, forward traversal, counters present
+    if (!pair || p.reverse_m || (p.M % (2 * BM)) || p.ring_rows <= 0 || (p.ring_rows % (2 * BM)) || p.ctr_done == nullptr ||
+        p.ctr_consumed == nullptr || (p.ring_mode != 1 && p.ring_mode != 2))
+      return cudaErrorInvalidValue;
+  }
   const bool ln = (p.epilogue == EPI_LN_BIAS_16 || p.epilogue == EPI_LN_BIAS_GELU_16);
   const bool out16 = (p.epilogue == EPI_BIAS_16 || p.epilogue == EPI_BIAS_GELU_16 || ln);
   if (ln && (p.ln_stats == nullptr || p.ln_s == nullptr || p.ln_nsb <= 0 || p.bias == nullptr)) return cudaErrorInvalidValue;
@@ -779,7 +812,7 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, co
   CUtensorMap out_map;
   if (out16 && tmap_c == nullptr) {  // the 16-bit epilogues store through TMA: 64-column x 32-row boxes over out16
     if (reinterpret_cast<uintptr_t>(p.out16) & 15) return cudaErrorInvalidValue;
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.N), static_cast<cuuint64_t>(p.M)};
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.N), static_cast<cuuint64_t>(p.ring_mode == 1 ? p.ring_rows : p.M)};
     cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p.ldo) * 2};
     cuuint32_t box[2] = {64, 32};
     cuuint32_t estr[2] = {1, 1};

@@ -70,6 +70,18 @@ struct GemmParams {
   // EPI_TOPK_32: candidate buffers [M, 2 * ceil(N / BN), TOPK_SLOTS]
   float* cand_val;
   int* cand_idx;
+  // Pipelined GEMM pair through an L2-resident ring (CTA pairs only; c_fc -> c_proj): the PRODUCER GEMM (ring_mode 1,
+  // 16-bit epilogue) stores its output rows modulo ring_rows, counts every finished epilogue warp of a 256-row pair-row in
+  // ctr_done[pair_row] once its TMA stores are complete, and before overwriting a ring slot waits until the consumer has
+  // counted need_consumed tiles of the pair-row ring_rows / 256 earlier in ctr_consumed.  The CONSUMER GEMM (ring_mode
+  // 2) loads its A rows modulo ring_rows after ctr_done[pair_row] reached need_done and counts every tile whose MMAs
+  // have completed in ctr_consumed[pair_row].  The two kernels run CONCURRENTLY on two streams, each on half of the SMs.
+  int ring_mode;
+  int ring_rows;
+  unsigned* ctr_done;
+  unsigned* ctr_consumed;
+  unsigned need_done;
+  unsigned need_consumed;
 };
 
 // Encodes a 2-D tiled tensor map over a row-major [rows, cols] 16-bit matrix with a {64, box_rows} box and

@@ -96,6 +96,32 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
 
+// ---------------------------------------------------------------- global progress counters between concurrent kernels
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin (with a short sleep) until *ctr >= need; bounded in the AIHAB_DEBUG_HANG build
+__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned need) {
+#ifdef AIHAB_DEBUG_HANG
+  for (unsigned spins = 0; ld_acquire_gpu(ctr) < need; ++spins) {
+    __nanosleep(100);
+    if (spins > (1u << 24)) {
+      printf("[aihab] progress counter wait timed out: block %d thread %d need %u have %u\n", static_cast<int>(blockIdx.x),
+             static_cast<int>(threadIdx.x), need, ld_acquire_gpu(ctr));
+      __trap();
+    }
+  }
+#else
+  while (ld_acquire_gpu(ctr) < need) __nanosleep(100);
+#endif
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

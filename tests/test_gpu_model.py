@@ -328,3 +328,22 @@ def test_sharded_extractor_host_copy_is_complete_on_return(tmp_path, cuda_device
     res2 = ext.run(array_source(u8[::-1].copy()), 37)
     assert torch.equal(res2["host_copy"][:37][:, :E], res2["features"].cpu())
     assert torch.equal(host[:, :E], res["features"].cpu())   # the clone taken after run() 1 is unaffected
+
+
+def test_pipelined_mlp_is_bit_identical(tmp_path, cuda_device, monkeypatch):
+    """AIHAB_MLP_PIPE=1: c_fc and c_proj run concurrently on half of the SMs each and hand the hidden activations over
+    through an L2-resident ring ordered by progress counters.  Same tiles, same arithmetic: features must equal the
+    sequential path bit for bit (512 images x 17 tokens = 34 pair-rows > the 32-pair-row ring, so slots are reused)."""
+    geom = GEOMETRIES["ViT-tiny/14"]
+    u8 = torch.from_numpy(synthetic_images_u8(512, 56)).to(cuda_device)
+    out = {}
+    for pipe in ("0", "1"):
+        monkeypatch.setenv("AIHAB_MLP_PIPE", pipe)
+        _, model, _ = load_model(tmp_path, geom.name, 1, cuda_device)
+        model.float()
+        model.visual.max_batch = 1024
+        out[pipe] = model.encode_image_u8(u8)
+        out[pipe + "b"] = model.encode_image_u8(u8)      # a second pass re-uses counters and ring
+        del model
+    assert torch.isfinite(out["1"]).all()
+    assert torch.equal(out["0"], out["1"]) and torch.equal(out["1"], out["1b"])
