@@ -377,6 +377,13 @@ struct aihab_vit {
   int ring_rows = 0;
   unsigned* mlp_ctr = nullptr;   // [2][cap_rows / 256] progress counters (done | consumed)
   CUtensorMap m_hring;           // A operand of c_proj over the ring
+  // AIHAB_MLP_FUSED=1: c_fc + c_proj as ONE kernel (mlp_fused_kernel) with the same ring / counters; tile lists per M
+  bool mlp_fused = false;
+  struct TileList {
+    std::vector<uint32_t> host;
+    uint32_t* dev = nullptr;
+  };
+  std::map<int, TileList> mlp_tiles;  // key: pair-rows (M / 256)
   size_t ws_bytes = 0;
   std::vector<void*> allocs;
 };
@@ -554,6 +561,49 @@ int run_blocks(aihab_vit* h, int n, cudaStream_t s) {
         return 1;
     }
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))   (clip/model.py:171-175,185)
+    if (h->mlp_fused && h->ln_fold && (M % 256) == 0 && M / 256 > h->ring_rows / 256 && h->num_sms >= 2) {
+      // ONE kernel: the two GEMMs' tiles interleaved on the whole machine, hidden activations through the L2 ring
+      const int pairs = M / 256, units = h->num_sms / 2;
+      aihab_vit::TileList& tl = h->mlp_tiles[pairs];
+      if (tl.dev == nullptr) {
+        const char* el = getenv("AIHAB_MLP_LAG");
+        const char* ex = getenv("AIHAB_MLP_EXTRA");
+        aihab::build_mlp_tiles(pairs, 4 * D / 256, D / 256, units, h->ring_rows / 256, &tl.host, el ? atoi(el) : 3,
+                               ex ? atoi(ex) : 4);
+        if (dev_alloc(h, reinterpret_cast<void**>(&tl.dev), tl.host.size() * sizeof(uint32_t))) return 1;
+        CK(cudaMemcpyAsync(tl.dev, tl.host.data(), tl.host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+      }
+      CK(cudaMemsetAsync(h->mlp_ctr, 0, 2 * (h->cap_rows / 256 + 1) * sizeof(unsigned), s));
+      aihab::MlpFusedParams fp{};
+      fp.M = M;
+      fp.D = D;
+      fp.ab_format = h->bf16;
+      fp.tiles = tl.dev;
+      fp.num_tiles = static_cast<int>(tl.host.size());
+      fp.ring_pairs = h->ring_rows / 256;
+      fp.ctr_done = h->mlp_ctr;
+      fp.ctr_cons = h->mlp_ctr + h->cap_rows / 256 + 1;
+      fp.need_done = static_cast<unsigned>((4 * D / 256) * 2 * 8);  // n tiles x 2 CTAs x 8 epilogue warps
+      fp.need_cons = static_cast<unsigned>((D / 256) * 2);          // n tiles x 2 CTAs
+      if (getenv("AIHAB_MLP_NOWAIT") != nullptr) fp.need_done = fp.need_cons = 0;  // DEBUG: wrong results, cost of the waits
+      fp.fc_bias = b.bp_fc;
+      fp.fc_s = b.s_fc;
+      fp.ln_stats = h->ln_stats;
+      fp.ln_nsb = nsb;
+      fp.proj_bias = b.b_proj;
+      if (l + 1 < layers) {
+        fp.ln_gamma = h->blocks[l + 1].ln1_g;
+        fp.a16_out = h->y2;
+        fp.stats_out = h->ln_stats;
+      }
+      {
+        ProfScope ps(PC_GEMM, 2.0 * M * (4.0 * D) * D * 2.0, s, -4 * D);
+        CKL(aihab::launch_mlp_fused(h->m_y2, b.m_fc[0], h->m_hring, b.m_proj[0], h->m_x, h->big, fp, h->num_sms, s));
+      }
+      nsb = (D + 127) / 128;
+      dir = 1;  // the fused kernel walks forward: its consumer starts from the freshest rows
+      continue;
+    }
     if (h->mlp_pipe && h->ln_fold && (M % 256) == 0 && M / 256 > h->ring_rows / 256 && h->num_sms >= 4) {
       // Pipelined pair: c_fc (stream s) and c_proj (side stream) run CONCURRENTLY, each on half of the SMs; c_fc's
       // 16-bit hidden rows go through a ring of h->ring_rows rows that stays in L2 (per-pair-row progress counters in
@@ -719,7 +769,11 @@ int build_stack(aihab_vit* h, int layers, const aihab_vit_block_weights* blocks,
   }
   {
     const char* e = getenv("AIHAB_MLP_PIPE");
-    const int ring = 8192;  // rows: 32 pair-rows x 4D x 2 B = 50 MB at D = 768
+    const char* ef = getenv("AIHAB_MLP_FUSED");
+    const bool fused = ef != nullptr && ef[0] == '1';
+    if (fused) e = ef;
+    int ring = 8192;  // rows: 32 pair-rows x 4D x 2 B = 50 MB at D = 768
+    if (const char* er = getenv("AIHAB_MLP_RING_PAIRS")) ring = 256 * std::max(4, atoi(er));
     if (e != nullptr && e[0] == '1' && h->ln_fold && (D % 256) == 0 && h->cap_rows > static_cast<size_t>(2 * ring)) {
       if (dev_alloc(h, reinterpret_cast<void**>(&h->mlp_ctr), 2 * (h->cap_rows / 256 + 1) * sizeof(unsigned))) return 1;
       if (aihab::make_tmap_2d_16bit(&h->m_hring, h->big, ring, 4 * D, static_cast<uint64_t>(4 * D) * 2, 128, h->bf16) !=
@@ -737,7 +791,8 @@ int build_stack(aihab_vit* h, int layers, const aihab_vit_block_weights* blocks,
         return 1;
       }
       h->ring_rows = ring;
-      h->mlp_pipe = true;
+      h->mlp_pipe = !fused;
+      h->mlp_fused = fused;
     }
   }
   if (h->attn_kind > 0) {

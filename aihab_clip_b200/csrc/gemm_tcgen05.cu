@@ -5,6 +5,9 @@
 
 #include <cudaTypedefs.h>
 
+#include <algorithm>
+#include <vector>
+
 namespace aihab {
 
 namespace {
@@ -651,6 +654,441 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused MLP: c_fc (LayerNorm fold + bias + QuickGELU, 16-bit hidden) and c_proj (+ fp32 residual, LayerNorm producer) as
+// ONE persistent kernel of CTA pairs on the whole machine.  The host hands it a tile list that interleaves the two
+// GEMMs' tiles so that a c_proj tile comes a few rounds after the c_fc tiles it reads: the [M, 4D] hidden activations
+// live in a ring of ring_pairs 256-row pair-rows that stays in L2 and never make the HBM round trip.  Per-pair-row
+// progress counters in global memory (release / acquire) order producers and consumers across CTAs.
+// Roles as in gemm_kernel; all 8 epilogue warps work on c_fc tiles, warps 4..7 run the residual rings of c_proj tiles.
+#ifndef AIHAB_FUSED_STAGES
+#define AIHAB_FUSED_STAGES 4
+#endif
+#ifndef AIHAB_FUSED_RING
+#define AIHAB_FUSED_RING 3
+#endif
+struct FusedSmem {
+  static constexpr int kStages = AIHAB_FUSED_STAGES;
+  static constexpr int kRS = AIHAB_FUSED_RING;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BM * BK * 2;  // half of the 256-wide W tile per CTA
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOffA = 0;
+  static constexpr int kOffB = kStages * kABytes;
+  static constexpr int kOffStaging = kStages * kStageBytes;  // 8 warps x 4 KB (c_fc); first 2 KB of warps 4..7: gamma * x transposition (c_proj)
+  static constexpr int kOffRing = kOffStaging + 8 * 4096;
+  static constexpr int kOffBias = kOffRing + 4 * kRS * RES_BOX;
+  static constexpr int kOffBars = kOffBias + 4 * 256 * 4;
+  static constexpr int kNumBars = 2 * kStages + 4 + 4 * kRS;
+  static constexpr int kOffTmemSlot = kOffBars + kNumBars * 8;
+  static constexpr int kTotal = kOffTmemSlot + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+  static_assert(kDynamic <= 227 * 1024, "shared memory budget");
+};
+
+constexpr uint32_t MLP_TILE_NONE = 0xffffffffu;
+
+__global__ void __launch_bounds__(384, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_wfc,
+                 const __grid_constant__ CUtensorMap tmap_hld, const __grid_constant__ CUtensorMap tmap_wproj,
+                 const __grid_constant__ CUtensorMap tmap_hst, const __grid_constant__ CUtensorMap tmap_x,
+                 const MlpFusedParams p) {
+  using L = FusedSmem;
+  constexpr int kStages = L::kStages;
+  constexpr int BN = 256;
+  constexpr int RS = L::kRS;
+  constexpr int CPT = BN / 32;  // residual boxes per c_proj tile and warp
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem + L::kOffA;
+  uint8_t* sB = smem + L::kOffB;
+  uint8_t* sStaging = smem + L::kOffStaging;
+  uint8_t* sRing = smem + L::kOffRing;
+  float* sBias = reinterpret_cast<float*>(smem + L::kOffBias);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* res_full_bar = tmem_empty_bar + 2;  // [4 warps][RS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmemSlot);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = static_cast<int>(ptx::cluster_ctarank());
+  const int unit = static_cast<int>(blockIdx.x >> 1);
+  const int num_units = static_cast<int>(gridDim.x >> 1);
+  const int num_tiles = p.num_tiles;
+  const int kb_fc = p.D / BK, kb_proj = 4 * p.D / BK;
+
+  ptx::griddep_launch();
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_y);
+    ptx::prefetch_tmap(&tmap_wfc);
+    ptx::prefetch_tmap(&tmap_hld);
+    ptx::prefetch_tmap(&tmap_wproj);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full_bar[i], 1);
+      ptx::mbar_init(&tmem_empty_bar[i], 8 * 2);  // one arrive per epilogue warp of the pair, whatever the tile type
+    }
+    for (int i = 0; i < 4 * RS; ++i) ptx::mbar_init(&res_full_bar[i], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_pair(tmem_slot, 2 * BN);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::griddep_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint64_t pol_w = ptx::policy_evict_last();
+      const uint64_t pol_a = ptx::policy_evict_normal();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = unit; i < num_tiles; i += num_units) {
+        const uint32_t d = __ldg(p.tiles + i);
+        if (d == MLP_TILE_NONE) continue;
+        const bool proj = (d >> 31) != 0;
+        const int pr = static_cast<int>((d >> 8) & 0x7fffffu), nb = static_cast<int>(d & 0xffu);
+        const CUtensorMap* ma = proj ? &tmap_hld : &tmap_y;
+        const CUtensorMap* mw = proj ? &tmap_wproj : &tmap_wfc;
+        int a_row = pr * (2 * BM) + cta_rank * BM;
+        const int num_kb = proj ? kb_proj : kb_fc;
+        if (proj) {  // every c_fc epilogue warp of this pair-row has finished its TMA stores
+          ptx::wait_counter(p.ctr_done + pr, p.need_done);
+          ptx::fence_proxy_async_all();
+          a_row = (pr % p.ring_pairs) * (2 * BM) + cta_rank * BM;
+        }
+        const int w_row = nb * BN + cta_rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          ptx::tma_load_2d_pair(sA + stage * L::kABytes, ma, &full_bar[stage], kb * BK, a_row, pol_a);
+          ptx::tma_load_2d_pair(sB + stage * L::kBBytes, mw, &full_bar[stage], kb * BK, w_row, pol_w);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, leader CTA only)
+    if (cta_rank == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(p.ab_format, 2 * BM, BN);
+      const uint32_t sA_u32 = ptx::smem_u32(sA), sB_u32 = ptx::smem_u32(sB);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int i = unit; i < num_tiles; i += num_units) {
+        const uint32_t d = __ldg(p.tiles + i);
+        if (d == MLP_TILE_NONE) continue;
+        const int num_kb = (d >> 31) ? kb_proj : kb_fc;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ++it;
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::make_kmajor_sw128_desc(sA_u32 + stage * L::kABytes);
+          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sB_u32 + stage * L::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            ptx::umma_f16_pair_w(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit_pair_w(&empty_bar[stage]);
+          if (kb == num_kb - 1) ptx::umma_commit_pair_w(&tmem_full_bar[as]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------ epilogue
+    constexpr int kEpiThreads = 256;
+    const int ew = warp & 3;
+    const int ehalf = (warp - EPI_WARP0) >> 2;
+    uint8_t* stg = sStaging + (warp - EPI_WARP0) * 4096;
+    const int et = threadIdx.x - EPI_WARP0 * 32;
+    const bool bf16 = p.ab_format != 0;
+    const bool ln_prod = p.ln_gamma != nullptr;
+    const int N_fc = 4 * p.D, N_proj = p.D;
+    // residual rings of warps 4..7 (ehalf == 0): boxes of this unit's c_proj tiles, prefetched RS-1 ahead across tiles
+    uint64_t* my_full = res_full_bar + ew * RS;
+    uint8_t* my_ring = sRing + ew * (RS * RES_BOX);
+    int pf_i = num_tiles, pf_c = 0;  // lane 0 of a ring warp: tile index / chunk of the next box to prefetch
+    int pf_q = 0;
+    auto pf_advance = [&]() {  // next c_proj tile of this unit after pf_i
+      do {
+        pf_i += num_units;
+      } while (pf_i < num_tiles && ((__ldg(p.tiles + pf_i) >> 31) == 0 || __ldg(p.tiles + pf_i) == MLP_TILE_NONE));
+    };
+    auto res_prefetch = [&]() {
+      if (pf_i >= num_tiles) return;
+      const uint32_t d = __ldg(p.tiles + pf_i);
+      const int pr = static_cast<int>((d >> 8) & 0x7fffffu), nb = static_cast<int>(d & 0xffu);
+      const int slot = pf_q % RS;
+      ptx::mbar_expect_tx(&my_full[slot], RES_BOX);
+      ptx::tma_load_2d(my_ring + slot * RES_BOX, &tmap_x, &my_full[slot], nb * BN + pf_c * 32,
+                       pr * (2 * BM) + cta_rank * BM + ew * 32);
+      ++pf_q;
+      if (++pf_c == CPT) {
+        pf_c = 0;
+        pf_advance();
+      }
+    };
+    int q = 0;
+    if (ehalf == 0 && lane == 0) {
+      pf_i = unit - num_units;
+      pf_advance();
+      for (int i = 0; i < RS - 1; ++i) res_prefetch();
+    }
+    // per-column vectors of the NEXT tile are fetched one tile ahead (see gemm_kernel)
+    float nxt_b, nxt_x;
+    auto fetch_cols = [&](int i) {
+      nxt_b = nxt_x = 0.0f;
+      while (i < num_tiles && __ldg(p.tiles + i) == MLP_TILE_NONE) i += num_units;
+      if (i >= num_tiles) return;
+      const uint32_t d = __ldg(p.tiles + i);
+      const int n = static_cast<int>(d & 0xffu) * BN + et;
+      if (d >> 31) {
+        nxt_b = __ldg(p.proj_bias + n);
+        if (ln_prod) nxt_x = __ldg(p.ln_gamma + n);
+      } else {
+        nxt_b = __ldg(p.fc_bias + n);
+        nxt_x = __ldg(p.fc_s + n);
+      }
+    };
+    fetch_cols(unit);
+    // Completion signal of a c_fc tile (this warp's TMA stores are in global memory -> ctr_done[pair-row] += 1).  Waiting
+    // for the stores right after issuing them would sit in front of the next epilogue, so the signal is deferred: to
+    // after the tmem_full wait of the next tile if that is a c_fc tile (its start waits for nothing this signal could
+    // hold up), and to the top of the next tile otherwise (a c_proj tile may depend, through other pairs, on this
+    // very signal; the list keeps >= 2 rounds between a pair-row's c_fc and c_proj tiles except in the final rounds).
+    int pend_pr = -1;
+    auto flush_done = [&]() {
+      if (pend_pr >= 0 && lane == 0) {
+        ptx::bulk_wait_all();
+        ptx::fence_proxy_async_all();
+        ptx::red_release_gpu_add(p.ctr_done + pend_pr, 1u);
+      }
+      pend_pr = -1;
+    };
+    int it = 0;
+    for (int i = unit; i < num_tiles; i += num_units) {
+      const uint32_t d = __ldg(p.tiles + i);
+      if (d == MLP_TILE_NONE) continue;
+      const bool proj = (d >> 31) != 0;
+      if (proj) flush_done();
+      const int pr = static_cast<int>((d >> 8) & 0x7fffffu), nb = static_cast<int>(d & 0xffu);
+      const int m0 = pr * (2 * BM) + cta_rank * BM + ew * 32;
+      const int n0 = nb * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      ++it;
+
+      float* sb = sBias + as * BN;
+      float* sx = sBias + (2 + as) * BN;
+      sb[et] = nxt_b;
+      sx[et] = nxt_x;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      fetch_cols(i + num_units);
+
+      float ln_r = 1.0f, ln_nrm = 0.0f;
+      if (!proj) {  // LayerNorm consumer statistics of this thread's row (see gemm_kernel)
+        const float* st = p.ln_stats + static_cast<size_t>(m0 + lane) * p.ln_nsb * 2;
+        float2 sv[kMaxStatBlocks];
+        float msum = 0.f;
+#pragma unroll
+        for (int b = 0; b < kMaxStatBlocks; ++b) {
+          if (b < p.ln_nsb) {
+            sv[b] = __ldg(reinterpret_cast<const float2*>(st) + b);
+            msum += sv[b].x;
+          }
+        }
+        const float mu = msum / static_cast<float>(p.ln_nsb);
+        float m2 = 0.f;
+#pragma unroll
+        for (int b = 0; b < kMaxStatBlocks; ++b) {
+          if (b < p.ln_nsb) {
+            const float dd = sv[b].x - mu;
+            m2 += fmaf(static_cast<float>(STAT_COLS) * dd, dd, sv[b].y);
+          }
+        }
+        const float var = fmaxf(m2 / static_cast<float>(p.D), 0.0f);
+        ln_r = rsqrtf(var + 1e-5f);
+        ln_nrm = -ln_r * mu;
+      }
+
+      if (!proj && pr >= p.ring_pairs) {  // the ring slot's previous pair-row must have been consumed
+        // (a BLOCKING wait never sits in front of a deferred completion signal: the consumer may be waiting for it)
+        const unsigned* cc = p.ctr_cons + pr - p.ring_pairs;
+        const bool block = __shfl_sync(0xffffffffu, lane == 0 && ptx::ld_acquire_gpu(cc) < p.need_cons, 0);
+        if (block) {
+          flush_done();
+          if (lane == 0) ptx::wait_counter(cc, p.need_cons);
+        }
+        if (lane == 0) ptx::fence_proxy_async_all();
+      }
+      ptx::mbar_wait(&tmem_full_bar[as], aphase);
+      ptx::tc_fence_after();
+      if (!proj) flush_done();  // the previous c_fc tile's stores completed while this tile's MMAs ran: free to count now
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+
+      if (!proj) {
+        // ---- c_fc tile: 64-column chunks dealt alternately to the two warps of a lane quadrant, TMA store into the ring
+        __syncwarp();
+        const int st_row = (pr % p.ring_pairs) * (2 * BM) + cta_rank * BM + ew * 32;
+#pragma unroll 1
+        for (int c = ehalf; c < BN / 64; c += 2) {
+          uint32_t ra[32], rb[32];
+          ptx::tmem_ld_32x32(taddr + c * 64, ra);
+          ptx::tmem_ld_32x32(taddr + c * 64 + 32, rb);
+          ptx::tmem_ld_wait();
+          if (c + 2 >= BN / 64) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
+          }
+          const float* cb = sb + c * 64;
+          const float* cx = sx + c * 64;
+          uint32_t pk[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v0 = __uint_as_float(j < 16 ? ra[2 * j] : rb[2 * j - 32]);
+            const float v1 = __uint_as_float(j < 16 ? ra[2 * j + 1] : rb[2 * j - 31]);
+            const float a0 = quick_gelu(fmaf(ln_r, v0, fmaf(ln_nrm, cx[2 * j], cb[2 * j])));
+            const float a1 = quick_gelu(fmaf(ln_r, v1, fmaf(ln_nrm, cx[2 * j + 1], cb[2 * j + 1])));
+            pk[j] = bf16 ? ptx::pack2<true>(a0, a1) : ptx::pack2<false>(a0, a1);
+          }
+          if (lane == 0) ptx::bulk_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) =
+                make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_hst, stg, n0 + c * 64, st_row);
+            ptx::bulk_commit();
+          }
+        }
+        pend_pr = pr;  // counted in ctr_done once the stores have completed (flush_done)
+      } else {
+        // ---- c_proj tile: every MMA has retired, so this CTA's A rows of the ring are consumed
+        if (warp == EPI_WARP0 && lane == 0) ptx::red_release_gpu_add(p.ctr_cons + pr, 1u);
+        if (ehalf == 0) {
+          if (ln_prod) {  // the gamma * x transposition reuses this warp's c_fc staging tile: its last TMA store has read it
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
+          }
+          float ln_s1 = 0.f, ln_s2 = 0.f, ln_piv = 0.f;
+          const int prow = m0 + lane;
+#pragma unroll 1
+          for (int c = 0; c < CPT; ++c, ++q) {
+            const int slot = q % RS;
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(taddr + c * 32, r);
+            ptx::mbar_wait(&my_full[slot], (q / RS) & 1);
+            ptx::tmem_ld_wait();
+            uint8_t* box = my_ring + slot * RES_BOX;
+            float4 xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = *reinterpret_cast<const float4*>(box + lane * 128 + ((u ^ (lane & 7)) << 4));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + 4 * u);
+              float4 v = xv[u];
+              v.x += __uint_as_float(r[4 * u]) + b4.x;
+              v.y += __uint_as_float(r[4 * u + 1]) + b4.y;
+              v.z += __uint_as_float(r[4 * u + 2]) + b4.z;
+              v.w += __uint_as_float(r[4 * u + 3]) + b4.w;
+              xv[u] = v;
+              if (ln_prod) {
+                if (u == 0 && (c & (STAT_COLS / 32 - 1)) == 0) ln_piv = v.x;
+                const float dx = v.x - ln_piv, dy = v.y - ln_piv, dz = v.z - ln_piv, dw = v.w - ln_piv;
+                ln_s1 += (dx + dy) + (dz + dw);
+                ln_s2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, ln_s2))));
+                const float4 g4 = *reinterpret_cast<const float4*>(sx + c * 32 + 4 * u);
+                r[2 * u] = bf16 ? ptx::pack2_sat<true>(g4.x * v.x, g4.y * v.y) : ptx::pack2_sat<false>(g4.x * v.x, g4.y * v.y);
+                r[2 * u + 1] = bf16 ? ptx::pack2_sat<true>(g4.z * v.z, g4.w * v.w) : ptx::pack2_sat<false>(g4.z * v.z, g4.w * v.w);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(box + lane * 128 + ((u ^ (lane & 7)) << 4)) = xv[u];
+            if (ln_prod) {
+              uint8_t* ast = stg;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                *reinterpret_cast<uint4*>(ast + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+              }
+              __syncwarp();
+              const int u = lane & 3;
+              const int gcol = n0 + c * 32 + u * 8;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int row = k * 8 + (lane >> 2);
+                const uint4 v = *reinterpret_cast<const uint4*>(ast + row * 64 + ((u ^ ((row >> 1) & 3)) << 4));
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.a16_out) + static_cast<size_t>(m0 + row) * N_proj + gcol) = v;
+              }
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&tmap_x, box, n0 + c * 32, m0);
+              ptx::bulk_commit();
+              ptx::bulk_wait_read<1>();
+              res_prefetch();
+            }
+            __syncwarp();
+            if (ln_prod && (c & (STAT_COLS / 32 - 1)) == STAT_COLS / 32 - 1) {
+              const int sblk = (n0 + c * 32) / STAT_COLS;
+              *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(prow) * (N_proj / STAT_COLS) + sblk) * 2) =
+                  make_float2(fmaf(ln_s1, 1.0f / STAT_COLS, ln_piv), fmaf(-ln_s1 * (1.0f / STAT_COLS), ln_s1, ln_s2));
+              ln_s1 = ln_s2 = 0.f;
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
+      }
+      (void)N_fc;
+    }
+    flush_done();
+    if (lane == 0) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, 2 * BN);
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 template <int BN, int EPI>
@@ -710,6 +1148,9 @@ cudaError_t gemm_init() {
   AIHAB_SET(128, EPI_BIAS_16) AIHAB_SET(128, EPI_BIAS_GELU_16) AIHAB_SET(128, EPI_BIAS_RES_32)
   AIHAB_SET(128, EPI_PATCH_32) AIHAB_SET(128, EPI_SCALE_32) AIHAB_SET(256, EPI_TOPK_32) AIHAB_SET(128, EPI_TOPK_32)
 #undef AIHAB_SET
+  if ((e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::kDynamic)) !=
+      cudaSuccess)
+    return e;
   return cudaSuccess;
 }
 
@@ -778,6 +1219,85 @@ cudaError_t make_tmap_2d_f32_box32(CUtensorMap* map, const void* base, uint64_t 
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+void build_mlp_tiles(int pair_rows, int n_fc, int n_proj, int units, int ring_pairs, std::vector<uint32_t>* out, int lag,
+                     int extra) {
+  lag = std::max(lag, 2);  // the deferred completion signal of a c_fc tile needs two rounds of slack (mlp_fused_kernel)
+  const long F = static_cast<long>(pair_rows) * n_fc, J = static_cast<long>(pair_rows) * n_proj;
+  // one balanced round of c_proj tiles closes the kernel (if the ring can hold that many pair-rows)
+  const long reserve = std::min<long>(std::min<long>(J, units), static_cast<long>(std::max(0, ring_pairs - 8)) * n_proj);
+  const int base = std::max(1, units * n_proj / (n_fc + n_proj));
+  std::vector<int> last_round(pair_rows, -1);  // round in which the pair-row's last c_fc tile was dealt
+  out->clear();
+  long f = 0, j = 0;
+  int start = 0;
+  for (int r = 0; f < F || j < J; ++r) {
+    const int eff_lag = f < F ? lag : 0;
+    long avail = 0;
+    for (long jj = j; jj < J; ++jj) {
+      const int lr = last_round[jj / n_proj];
+      if (lr < 0 || lr > r - eff_lag) break;
+      ++avail;
+    }
+    // a c_fc tile of pair-row pr overwrites the ring slot of pr - ring_pairs: deal it only after every c_proj tile of
+    // that pair-row was dealt in an EARLIER round (deadlock freedom: waits only ever point to earlier rounds)
+    const long fc_pr_limit = ring_pairs + j / n_proj;
+    long quota;
+    if (f < F) {
+      const long cap = std::max<long>(0, (J - reserve) - j);
+      quota = std::min<long>(std::min(avail, cap), base + (avail > base ? extra : 0));
+    } else {
+      quota = std::min<long>(avail, units);
+    }
+    const size_t row0 = out->size();
+    out->resize(row0 + units, MLP_TILE_NONE);
+    std::vector<char> chosen(units, 0);
+    for (long k = 0; k < quota; ++k) chosen[(start + k) % units] = 1;
+    start = static_cast<int>((start + quota) % units);
+    long taken = 0;
+    for (int u = 0; u < units; ++u) {
+      const bool fc_ok = f < F && f / n_fc < fc_pr_limit;
+      if (j < J && taken < avail && (chosen[u] || !fc_ok)) {
+        (*out)[row0 + u] = 0x80000000u | (static_cast<uint32_t>(j / n_proj) << 8) | static_cast<uint32_t>(j % n_proj);
+        ++j;
+        ++taken;
+      } else if (fc_ok) {
+        const int pr = static_cast<int>(f / n_fc), n = static_cast<int>(f % n_fc);
+        (*out)[row0 + u] = (static_cast<uint32_t>(pr) << 8) | static_cast<uint32_t>(n);
+        ++f;
+        if (n == n_fc - 1) last_round[pr] = r;
+      }
+    }
+  }
+}
+
+cudaError_t launch_mlp_fused(const CUtensorMap& tmap_y, const CUtensorMap& tmap_wfc, const CUtensorMap& tmap_hld,
+                             const CUtensorMap& tmap_wproj, const CUtensorMap& tmap_x, void* ring_base,
+                             const MlpFusedParams& p, int num_sms, cudaStream_t stream) {
+  if (p.M <= 0 || (p.M % (2 * BM)) || p.D <= 0 || (p.D % 256) || p.D / STAT_COLS > kMaxStatBlocks || p.tiles == nullptr ||
+      p.num_tiles <= 0 || p.ring_pairs <= 0 || p.ctr_done == nullptr || p.ctr_cons == nullptr || p.fc_bias == nullptr ||
+      p.fc_s == nullptr || p.ln_stats == nullptr || p.ln_nsb <= 0 || p.ln_nsb > kMaxStatBlocks || p.proj_bias == nullptr ||
+      4 * p.D / 256 > 255 || num_sms < 2 || (reinterpret_cast<uintptr_t>(ring_base) & 15))
+    return cudaErrorInvalidValue;
+  if (p.ln_gamma != nullptr && (p.a16_out == nullptr || p.stats_out == nullptr)) return cudaErrorInvalidValue;
+  if (g_encode == nullptr) {
+    cudaError_t e = gemm_init();
+    if (e != cudaSuccess) return e;
+  }
+  CUtensorMap hst;  // 64-column x 32-row store boxes over the ring
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(4 * p.D), static_cast<cuuint64_t>(p.ring_pairs) * 2 * BM};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(4 * p.D) * 2};
+  cuuint32_t box[2] = {64, 32};
+  cuuint32_t estr[2] = {1, 1};
+  if (g_encode(&hst, p.ab_format ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ring_base, gdim,
+               gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorInvalidValue;
+  const int units = num_sms / 2;
+  if (p.num_tiles % units) return cudaErrorInvalidValue;  // the list was built for this many pairs
+  return launch_kernel(mlp_fused_kernel, 2 * units, 384, FusedSmem::kDynamic, stream, 2, true, tmap_y, tmap_wfc, tmap_hld,
+                       tmap_wproj, hst, tmap_x, p);
+}
+
 bool gemm_use_pair(int M, int N, int num_sms) {
   // CTA pairs finish a 256-wide tile ~5 % faster (half the W traffic per SM) but schedule in units of two M blocks:
   // take them unless wave quantisation costs more than that.
@@ -839,3 +1359,14 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, co
 }
 
 }  // namespace aihab
+
+// Debug export (not part of include/aihab_clip.h): the fused-MLP tile list for the CPU tests of its invariants.
+// Returns the number of entries (rounds x units); writes min(cap, entries) of them.
+extern "C" __attribute__((visibility("default"))) long aihab_debug_mlp_tiles(int pair_rows, int n_fc, int n_proj, int units,
+                                                                             int ring_pairs, uint32_t* out, long cap) {
+  if (pair_rows <= 0 || n_fc <= 0 || n_proj <= 0 || units <= 0 || ring_pairs <= 0 || n_fc > 255 || n_proj > 255) return -1;
+  std::vector<uint32_t> v;
+  aihab::build_mlp_tiles(pair_rows, n_fc, n_proj, units, ring_pairs, &v);
+  for (long i = 0; i < cap && i < static_cast<long>(v.size()); ++i) out[i] = v[i];
+  return static_cast<long>(v.size());
+}

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace aihab {
 
 enum GemmEpilogue : int {
@@ -83,6 +85,38 @@ struct GemmParams {
   unsigned need_done;
   unsigned need_consumed;
 };
+
+// Fused MLP (c_fc -> QuickGELU -> c_proj + residual as ONE persistent kernel of CTA pairs; gemm_tcgen05.cu
+// mlp_fused_kernel).  M must be a multiple of 256 and D of 256.
+struct MlpFusedParams {
+  int M, D;               // token rows, width (hidden = 4 D)
+  int ab_format;
+  const uint32_t* tiles;  // device tile list from build_mlp_tiles(): bit 31 = c_proj, bits 8..30 pair-row, bits 0..7 n tile
+  int num_tiles;          // entries (rounds x units; MLP_TILE_NONE pads)
+  int ring_pairs;         // pair-rows (256 rows each) in the hidden ring
+  unsigned* ctr_done;     // [M / 256] c_fc epilogue warps finished per pair-row (zeroed before the launch)
+  unsigned* ctr_cons;     // [M / 256] c_proj tiles whose MMAs retired per pair-row (zeroed before the launch)
+  unsigned need_done, need_cons;
+  const float* fc_bias;   // b' of the LayerNorm fold
+  const float* fc_s;      // s_n of the LayerNorm fold
+  const float* ln_stats;  // [M, ln_nsb, 2] from the previous residual GEMM
+  int ln_nsb;
+  const float* proj_bias;
+  const float* ln_gamma;  // optional LayerNorm producer for the next block (nullptr: none)
+  void* a16_out;
+  float* stats_out;
+};
+// Tile list for `units` CTA pairs: entry r * units + u is the r-th tile of pair u.  c_proj tiles follow the c_fc tiles
+// of their pair-row by >= lag rounds, are spread evenly over the pairs, and one full round of them is kept for the end
+// so that the tail is balanced; a c_fc tile is dealt only after the c_proj tiles of the pair-row ring_pairs earlier, so
+// every wait points to an earlier round (tools/probes/mlp_tiles_sim.py replays the schedule).
+void build_mlp_tiles(int pair_rows, int n_fc, int n_proj, int units, int ring_pairs, std::vector<uint32_t>* out, int lag = 3,
+                     int extra = 4);
+// tmap_y: A of c_fc {64,128}; tmap_wfc / tmap_wproj: W halves {64,128}; tmap_hld: ring as A of c_proj {64,128};
+// tmap_x: make_tmap_2d_f32_box32 over the residual.  The store map over the ring is built here from ring_base.
+cudaError_t launch_mlp_fused(const CUtensorMap& tmap_y, const CUtensorMap& tmap_wfc, const CUtensorMap& tmap_hld,
+                             const CUtensorMap& tmap_wproj, const CUtensorMap& tmap_x, void* ring_base,
+                             const MlpFusedParams& p, int num_sms, cudaStream_t stream);
 
 // Encodes a 2-D tiled tensor map over a row-major [rows, cols] 16-bit matrix with a {64, box_rows} box and
 // SWIZZLE_128B.  row_pitch_bytes must be a multiple of 16.  Returns cudaSuccess or an error.

@@ -330,15 +330,19 @@ def test_sharded_extractor_host_copy_is_complete_on_return(tmp_path, cuda_device
     assert torch.equal(host[:, :E], res["features"].cpu())   # the clone taken after run() 1 is unaffected
 
 
-def test_pipelined_mlp_is_bit_identical(tmp_path, cuda_device, monkeypatch):
+@pytest.mark.parametrize("mode,ring_pairs", [("AIHAB_MLP_PIPE", None), ("AIHAB_MLP_FUSED", None), ("AIHAB_MLP_FUSED", "6")])
+def test_pipelined_mlp_is_bit_identical(tmp_path, cuda_device, monkeypatch, mode, ring_pairs):
     """AIHAB_MLP_PIPE=1: c_fc and c_proj run concurrently on half of the SMs each and hand the hidden activations over
-    through an L2-resident ring ordered by progress counters.  Same tiles, same arithmetic: features must equal the
-    sequential path bit for bit (512 images x 17 tokens = 34 pair-rows > the 32-pair-row ring, so slots are reused)."""
+    through an L2-resident ring ordered by progress counters.  AIHAB_MLP_FUSED=1: both GEMMs' tiles interleaved in ONE
+    persistent kernel (mlp_fused_kernel) over the same ring.  Same tiles, same arithmetic: features must equal the
+    sequential path bit for bit (512 images x 17 tokens = 34 pair-rows > the ring, so slots are reused)."""
     geom = GEOMETRIES["ViT-tiny/14"]
     u8 = torch.from_numpy(synthetic_images_u8(512, 56)).to(cuda_device)
+    if ring_pairs is not None:
+        monkeypatch.setenv("AIHAB_MLP_RING_PAIRS", ring_pairs)
     out = {}
     for pipe in ("0", "1"):
-        monkeypatch.setenv("AIHAB_MLP_PIPE", pipe)
+        monkeypatch.setenv(mode, pipe)
         _, model, _ = load_model(tmp_path, geom.name, 1, cuda_device)
         model.float()
         model.visual.max_batch = 1024
