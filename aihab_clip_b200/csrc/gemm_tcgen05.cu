@@ -6,6 +6,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace aihab {
@@ -19,6 +20,12 @@ constexpr int EPI_WARP0 = 4;  // warps 4.. are the epilogue (warp % 4 selects th
 // Two warps per TMEM lane quadrant (8 epilogue warps, 384 threads) so the epilogue keeps up with the MMA.  The fp32
 // residual epilogue streams 4 KB TMA boxes through per-warp rings, one warp per quadrant (two per quadrant were
 // measured no faster in round 1: in the step these GEMMs wait for DRAM, not for the epilogue warps).
+// EPI_RES_WIDE (internal, CTA pairs only): EPI_BIAS_RES_32 with TWO warps per quadrant (8 rings of 3 boxes) and 3 operand
+// stages, for the residual GEMM with a SHORT main loop (out_proj, K = D): there the tile time is the latency chain of
+// the residual epilogue (one warp per scheduler issues 25 % of the time), so a second chain per scheduler pays
+// (-10 % on out_proj in the step), while c_proj (K = 4 D) is main-loop bound and keeps 4 stages + 4 deep rings.
+constexpr int EPI_RES_WIDE = 100;
+__host__ __device__ constexpr bool is_res(int epi) { return epi == EPI_BIAS_RES_32 || epi == EPI_RES_WIDE; }
 __host__ __device__ constexpr int epi_warps(int epi, bool two) {
   (void)two;
   return epi == EPI_BIAS_RES_32 ? 4 : 8;
@@ -31,20 +38,27 @@ constexpr int kMaxStatBlocks = 8;  // width <= 1024 (api.cu allocates the statis
 
 template <int BN, int EPI, bool TWO>
 struct SmemLayout {
-  static constexpr bool kRes = (EPI == EPI_BIAS_RES_32);
+  static constexpr bool kRes = is_res(EPI);
+  static constexpr bool kWide = (EPI == EPI_RES_WIDE);
   // the residual epilogue trades operand stages for a 64 KB TMA ring: those GEMMs are bound by the fp32 residual
   // read-modify-write, not by the MMA pipe.  In a CTA pair each CTA stages only half of the W tile.
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
-  static constexpr int kResWarps = epi_warps(EPI_BIAS_RES_32, TWO);  // residual epilogue warps (rings)
+  static constexpr int kResWarps = kWide ? 8 : 4;  // residual epilogue warps (rings)
 #ifndef AIHAB_RES_RING
 #define AIHAB_RES_RING 4
 #endif
 #ifndef AIHAB_RES_STAGES
 #define AIHAB_RES_STAGES 4
 #endif
-  static constexpr int kRS = TWO ? AIHAB_RES_RING : 4;  // ring slots per residual epilogue warp (kRS - 1 boxes in flight)
-  static constexpr int kStages =
+#ifndef AIHAB_WIDE_RING
+#define AIHAB_WIDE_RING 3
+#endif
+#ifndef AIHAB_WIDE_STAGES
+#define AIHAB_WIDE_STAGES 3
+#endif
+  static constexpr int kRS = kWide ? AIHAB_WIDE_RING : (TWO ? AIHAB_RES_RING : 4);  // ring slots per residual epilogue warp (kRS - 1 boxes in flight)
+  static constexpr int kStages = kWide ? AIHAB_WIDE_STAGES :
       TWO ? (kRes ? AIHAB_RES_STAGES : 5) : ((BN == 256) ? 3 : (kRes ? (AIHAB_RES_STAGES < 4 ? AIHAB_RES_STAGES : 4) : 5));
   static constexpr int kStageBytes = kABytes + kBBytes;
   // residual rings (kResWarps x kRS boxes) + 2 KB per warp for the coalesced gamma*x store | 8 warps x 4 KB staging tile
@@ -81,11 +95,12 @@ __device__ __forceinline__ float quick_gelu(float x) {
 // TWO = CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, UMMA M = 256; each CTA loads its own
 // 128 A rows and HALF of the W tile (the pair's MMA reads both halves), owns the accumulator rows of its A rows and
 // runs its own epilogue.  Halves the W shared-memory fill and L2 -> SM traffic per FLOP.
-template <int BN, int EPI, bool TWO>
-__global__ void __launch_bounds__(num_threads(EPI, TWO), 1)
+template <int BN, int EPI_, bool TWO>
+__global__ void __launch_bounds__(num_threads(EPI_, TWO), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
-  using L = SmemLayout<BN, EPI, TWO>;
+  using L = SmemLayout<BN, EPI_, TWO>;
+  constexpr int EPI = (EPI_ == EPI_RES_WIDE) ? static_cast<int>(EPI_BIAS_RES_32) : EPI_;  // same arithmetic, wider warp layout
   constexpr int kStages = L::kStages;
   constexpr bool kLn = (EPI == EPI_LN_BIAS_16 || EPI == EPI_LN_BIAS_GELU_16);
   constexpr bool kGelu = (EPI == EPI_BIAS_GELU_16 || EPI == EPI_LN_BIAS_GELU_16);
@@ -133,7 +148,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
-      ptx::mbar_init(&tmem_empty_bar[i], epi_warps(EPI, TWO) * (TWO ? 2 : 1));  // one arrive per epilogue warp (of the pair)
+      ptx::mbar_init(&tmem_empty_bar[i], epi_warps(EPI_, TWO) * (TWO ? 2 : 1));  // one arrive per epilogue warp (of the pair)
     }
     for (int i = 0; i < L::kResWarps * L::kRS; ++i) ptx::mbar_init(&res_full_bar[i], 1);
     ptx::fence_mbar_init();
@@ -245,7 +260,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------ epilogue
-    constexpr int kEpiThreads = epi_warps(EPI, TWO) * 32;
+    constexpr int kEpiThreads = epi_warps(EPI_, TWO) * 32;
     const int ew = warp & 3;                   // TMEM lanes [32*ew, 32*ew+32) (hardware: warp % 4)
     const int ehalf = (warp - EPI_WARP0) >> 2;  // 0, or 0/1 when two warps share a quadrant
     uint8_t* stg = sStaging + (warp - EPI_WARP0) * 4096;  // 16-bit / plain fp32 epilogues (not the residual rings)
@@ -1112,13 +1127,28 @@ cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
                        1, true, ta, tw, tc, p);
 }
 
+// the wide residual epilogue pays when the main loop is short (see EPI_RES_WIDE); AIHAB_RES_WIDE=0 disables it
+bool res_wide(const GemmParams& p) {
+  static const bool enabled = [] {
+    const char* e = getenv("AIHAB_RES_WIDE");
+    return e == nullptr || e[0] != '0';
+  }();
+  return enabled && p.K <= 1024 && p.ring_mode == 0;
+}
+
 template <int BN>
 cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const GemmParams& p,
                       int grid, bool pair, cudaStream_t stream) {
   switch (p.epilogue) {
     case EPI_BIAS_16: return launch_one<BN, EPI_BIAS_16>(ta, tw, tc, p, grid, pair, stream);
     case EPI_BIAS_GELU_16: return launch_one<BN, EPI_BIAS_GELU_16>(ta, tw, tc, p, grid, pair, stream);
-    case EPI_BIAS_RES_32: return launch_one<BN, EPI_BIAS_RES_32>(ta, tw, tc, p, grid, pair, stream);
+    case EPI_BIAS_RES_32:
+      if constexpr (BN == 256) {
+        if (pair && res_wide(p))
+          return launch_kernel(gemm_kernel<256, EPI_RES_WIDE, true>, grid, num_threads(EPI_RES_WIDE, true),
+                               SmemLayout<256, EPI_RES_WIDE, true>::kDynamic, stream, 2, true, ta, tw, tc, p);
+      }
+      return launch_one<BN, EPI_BIAS_RES_32>(ta, tw, tc, p, grid, pair, stream);
     case EPI_PATCH_32: return launch_one<BN, EPI_PATCH_32>(ta, tw, tc, p, grid, pair, stream);
     case EPI_SCALE_32: return launch_one<BN, EPI_SCALE_32>(ta, tw, tc, p, grid, pair, stream);
     case EPI_LN_BIAS_16: return launch_one<BN, EPI_LN_BIAS_16>(ta, tw, tc, p, grid, pair, stream);
@@ -1148,6 +1178,9 @@ cudaError_t gemm_init() {
   AIHAB_SET(128, EPI_BIAS_16) AIHAB_SET(128, EPI_BIAS_GELU_16) AIHAB_SET(128, EPI_BIAS_RES_32)
   AIHAB_SET(128, EPI_PATCH_32) AIHAB_SET(128, EPI_SCALE_32) AIHAB_SET(256, EPI_TOPK_32) AIHAB_SET(128, EPI_TOPK_32)
 #undef AIHAB_SET
+  if ((e = cudaFuncSetAttribute(gemm_kernel<256, EPI_RES_WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SmemLayout<256, EPI_RES_WIDE, true>::kDynamic)) != cudaSuccess)
+    return e;
   if ((e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::kDynamic)) !=
       cudaSuccess)
     return e;

@@ -2,8 +2,9 @@
 import glob
 import json
 import os
+import sys
 
-for f in sorted(glob.glob("gpurun_out/fused/bench_*.json"), key=os.path.getmtime):
+for f in sorted(glob.glob((sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/fused") + "/bench_*.json"), key=os.path.getmtime):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
     except Exception as e:  # noqa: BLE001
