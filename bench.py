@@ -537,7 +537,9 @@ def run_b200(args):
             M_tok, Dw, pp = B * geom.tokens, geom.vision_width, geom.vision_patch_size
             names = {(2.0 * M_tok * 3 * Dw * Dw, 3 * Dw): "qkv", (2.0 * M_tok * Dw * Dw, Dw): "out_proj",
                      (2.0 * M_tok * 4 * Dw * Dw, 4 * Dw): "c_fc", (2.0 * M_tok * 4 * Dw * Dw, Dw): "c_proj",
-                     (2.0 * B * geom.grid ** 2 * Dw * (-(-3 * pp * pp // 64) * 64), Dw): "patch_embed"}
+                     (2.0 * B * geom.grid ** 2 * Dw * (-(-3 * pp * pp // 64) * 64), Dw): "patch_embed",
+                     # opt-in experiments (AIHAB_MLP_PIPE / AIHAB_MLP_FUSED): both MLP GEMMs timed as one site
+                     (2.0 * M_tok * 4 * Dw * Dw * 2.0, -4 * Dw): "c_fc+c_proj"}
             kernels["gemm"]["sites"] = {
                 names.get((sr["work"], sr["tag"]), "N=%d work=%.4g" % (sr["tag"], sr["work"])): {
                     "launches": sr["launches"], "avg_ms": sr["ms"] / sr["launches"],
