@@ -1302,6 +1302,7 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
     p.scale = scale;
     if (fused) {
       p.epilogue = aihab::EPI_TOPK_32;
+      p.topk_k = k;
       p.cand_val = cand_val_t.p;
       p.cand_idx = cand_idx_t.p;
       CKL(aihab::launch_gemm(ma, mw, nullptr, p, bn, sms, s));

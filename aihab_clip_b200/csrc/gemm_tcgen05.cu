@@ -25,6 +25,9 @@ constexpr int EPI_WARP0 = 4;  // warps 4.. are the epilogue (warp % 4 selects th
 // the residual epilogue (one warp per scheduler issues 25 % of the time), so a second chain per scheduler pays
 // (-10 % on out_proj in the step), while c_proj (K = 4 D) is main-loop bound and keeps 4 stages + 4 deep rings.
 constexpr int EPI_RES_WIDE = 100;
+// EPI_TOPK5 (internal): EPI_TOPK_32 keeping 5 instead of TOPK_SLOTS candidates per (row, warp) - enough for k <= 5 and
+// 40 % fewer instructions in the branch-free insertion chain (the epilogue of the K = 3E logits GEMM must stay hidden)
+constexpr int EPI_TOPK5 = 101;
 __host__ __device__ constexpr bool is_res(int epi) { return epi == EPI_BIAS_RES_32 || epi == EPI_RES_WIDE; }
 __host__ __device__ constexpr int epi_warps(int epi, bool two) {
   (void)two;
@@ -100,7 +103,8 @@ __global__ void __launch_bounds__(num_threads(EPI_, TWO), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   using L = SmemLayout<BN, EPI_, TWO>;
-  constexpr int EPI = (EPI_ == EPI_RES_WIDE) ? static_cast<int>(EPI_BIAS_RES_32) : EPI_;  // same arithmetic, wider warp layout
+  constexpr int EPI = (EPI_ == EPI_RES_WIDE) ? static_cast<int>(EPI_BIAS_RES_32)   // same arithmetic, wider warp layout
+                      : (EPI_ == EPI_TOPK5) ? static_cast<int>(EPI_TOPK_32) : EPI_;
   constexpr int kStages = L::kStages;
   constexpr bool kLn = (EPI == EPI_LN_BIAS_16 || EPI == EPI_LN_BIAS_GELU_16);
   constexpr bool kGelu = (EPI == EPI_BIAS_GELU_16 || EPI == EPI_LN_BIAS_GELU_16);
@@ -541,12 +545,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
         if constexpr (EPI == EPI_TOPK_32) {
-          // running top-TOPK_SLOTS of this thread's accumulator row over the warp's chunks of the tile; columns arrive
-          // in ascending order, so a strict '>' keeps the lower column ahead among equal values (torch.topk order)
-          float tv[TOPK_SLOTS];
-          int ti[TOPK_SLOTS];
+          // running top-S of this thread's accumulator row over the warp's chunks of the tile; columns arrive in
+          // ascending order, so a strict '>' keeps the lower column ahead among equal values (torch.topk order).
+          // BRANCH-FREE insertion (compare / select chain, ~5 instructions per slot and element): lanes hold different
+          // rows, so a data-dependent insertion branch is taken by some lane for almost every element and the warp
+          // pays the slow path every time (measured: 148 -> see DESIGN 4.4 per 32 k-row pass).
+          constexpr int S = (EPI_ == EPI_TOPK5) ? 5 : TOPK_SLOTS;
+          float tv[S];
+          int ti[S];
 #pragma unroll
-          for (int i = 0; i < TOPK_SLOTS; ++i) {
+          for (int i = 0; i < S; ++i) {
             tv[i] = -INFINITY;
             ti[i] = 0x7fffffff;
           }
@@ -558,31 +566,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int col0 = n0 + c * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float v = fmaf(__uint_as_float(r[j]), p.scale, sb[c * 32 + j]);
-              if (col0 + j < p.N && v > tv[TOPK_SLOTS - 1]) {
-                tv[TOPK_SLOTS - 1] = v;
-                ti[TOPK_SLOTS - 1] = col0 + j;
+              const int col = col0 + j;
+              const float v = col < p.N ? fmaf(__uint_as_float(r[j]), p.scale, sb[c * 32 + j]) : -INFINITY;
 #pragma unroll
-                for (int i = TOPK_SLOTS - 1; i > 0; --i) {
-                  if (tv[i] > tv[i - 1]) {
-                    const float fv = tv[i];
-                    tv[i] = tv[i - 1];
-                    tv[i - 1] = fv;
-                    const int iv = ti[i];
-                    ti[i] = ti[i - 1];
-                    ti[i - 1] = iv;
-                  }
-                }
+              for (int i = S - 1; i >= 1; --i) {
+                const bool ci = v > tv[i], cm = v > tv[i - 1];
+                ti[i] = cm ? ti[i - 1] : (ci ? col : ti[i]);
+                tv[i] = cm ? tv[i - 1] : (ci ? v : tv[i]);
               }
+              const bool c0 = v > tv[0];
+              ti[0] = c0 ? col : ti[0];
+              tv[0] = c0 ? v : tv[0];
             }
           }
           const int grow = m0 + lane;
           if (grow < p.M) {
             const size_t base = (static_cast<size_t>(grow) * (2 * n_blocks) + 2 * (n0 / BN) + ehalf) * TOPK_SLOTS;
+            float ov[TOPK_SLOTS];
+            int oi[TOPK_SLOTS];
+#pragma unroll
+            for (int i = 0; i < TOPK_SLOTS; ++i) {
+              ov[i] = i < S ? tv[i < S ? i : 0] : -INFINITY;
+              oi[i] = i < S ? ti[i < S ? i : 0] : 0x7fffffff;
+            }
 #pragma unroll
             for (int i = 0; i < TOPK_SLOTS; i += 4) {
-              *reinterpret_cast<float4*>(p.cand_val + base + i) = make_float4(tv[i], tv[i + 1], tv[i + 2], tv[i + 3]);
-              *reinterpret_cast<int4*>(p.cand_idx + base + i) = make_int4(ti[i], ti[i + 1], ti[i + 2], ti[i + 3]);
+              *reinterpret_cast<float4*>(p.cand_val + base + i) = make_float4(ov[i], ov[i + 1], ov[i + 2], ov[i + 3]);
+              *reinterpret_cast<int4*>(p.cand_idx + base + i) = make_int4(oi[i], oi[i + 1], oi[i + 2], oi[i + 3]);
             }
           }
         } else {
@@ -1153,7 +1163,9 @@ cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, const CUtens
     case EPI_SCALE_32: return launch_one<BN, EPI_SCALE_32>(ta, tw, tc, p, grid, pair, stream);
     case EPI_LN_BIAS_16: return launch_one<BN, EPI_LN_BIAS_16>(ta, tw, tc, p, grid, pair, stream);
     case EPI_LN_BIAS_GELU_16: return launch_one<BN, EPI_LN_BIAS_GELU_16>(ta, tw, tc, p, grid, pair, stream);
-    case EPI_TOPK_32: return launch_one<BN, EPI_TOPK_32>(ta, tw, tc, p, grid, pair, stream);
+    case EPI_TOPK_32:
+      if (p.topk_k >= 1 && p.topk_k <= 5) return launch_one<BN, EPI_TOPK5>(ta, tw, tc, p, grid, pair, stream);
+      return launch_one<BN, EPI_TOPK_32>(ta, tw, tc, p, grid, pair, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -1177,6 +1189,7 @@ cudaError_t gemm_init() {
   AIHAB_SET(256, EPI_LN_BIAS_GELU_16) AIHAB_SET(128, EPI_LN_BIAS_16) AIHAB_SET(128, EPI_LN_BIAS_GELU_16)
   AIHAB_SET(128, EPI_BIAS_16) AIHAB_SET(128, EPI_BIAS_GELU_16) AIHAB_SET(128, EPI_BIAS_RES_32)
   AIHAB_SET(128, EPI_PATCH_32) AIHAB_SET(128, EPI_SCALE_32) AIHAB_SET(256, EPI_TOPK_32) AIHAB_SET(128, EPI_TOPK_32)
+  AIHAB_SET(256, EPI_TOPK5) AIHAB_SET(128, EPI_TOPK5)
 #undef AIHAB_SET
   if ((e = cudaFuncSetAttribute(gemm_kernel<256, EPI_RES_WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 SmemLayout<256, EPI_RES_WIDE, true>::kDynamic)) != cudaSuccess)

@@ -72,6 +72,7 @@ struct GemmParams {
   // EPI_TOPK_32: candidate buffers [M, 2 * ceil(N / BN), TOPK_SLOTS]
   float* cand_val;
   int* cand_idx;
+  int topk_k;  // the k the caller needs (1..TOPK_SLOTS; 0 = TOPK_SLOTS): k <= 5 keeps 5 candidates per slot group
   // Pipelined GEMM pair through an L2-resident ring (CTA pairs only; c_fc -> c_proj): the PRODUCER GEMM (ring_mode 1,
   // 16-bit epilogue) stores its output rows modulo ring_rows, counts every finished epilogue warp of a 256-row pair-row in
   // ctr_done[pair_row] once its TMA stores are complete, and before overwriting a ring slot waits until the consumer has
