@@ -1168,6 +1168,21 @@ int aihab_score(const float* feats, int n, int D, const float* proj, int E, cons
   const int dev = device_of(feats);
   DeviceGuard guard(dev);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(feats) | reinterpret_cast<uintptr_t>(proj) | reinterpret_cast<uintptr_t>(text_w) |
+                           reinterpret_cast<uintptr_t>(emb_out) | reinterpret_cast<uintptr_t>(logits_out)) & 15) == 0;
+  if (text_w != nullptr && aligned16 && aihab::score_mid_supported(n, D, E, C)) {
+    // one extraction batch (the headline step's 256 rows): column-sliced projection and logits, then the top-k kernel
+    keep_pool_warm(dev);
+    AsyncTemp<float> raw_t(s), logit_t(s);
+    if (proj != nullptr) CK(raw_t.alloc(static_cast<size_t>(n) * E * 4));
+    if (logits_out == nullptr) CK(logit_t.alloc(static_cast<size_t>(n) * C * 4));
+    float* lg = logits_out ? logits_out : logit_t.p;
+    ProfScope ps(PC_SCORE, 2.0 * n * (static_cast<double>(D) * E + static_cast<double>(E) * C), s);
+    CKL(aihab::launch_score_mid(feats, n, D, proj, E, text_w, C, scale, raw_t.p, emb_out, lg, s));
+    if (proj != nullptr) g_launches += 1;  // two kernels
+    if (k > 0) CKL(aihab::launch_topk(lg, n, C, k, topk_idx, topk_val, s));
+    return 0;
+  }
   if (aihab::score_fused_supported(n, D, E, text_w ? C : 0)) {
     ProfScope ps(PC_SCORE, 2.0 * n * (static_cast<double>(proj ? D : 0) * E + static_cast<double>(text_w ? E : 0) * C), s);
     CKL(aihab::launch_score_fused(feats, n, D, proj, E, text_w, C, scale, k, emb_out, logits_out, topk_idx, topk_val, s));

@@ -125,6 +125,11 @@ cudaError_t launch_topk_merge(const float* cand_val, const int* cand_idx, int ro
                               float* val, cudaStream_t stream);
 
 // One-launch small-batch scoring (n <= 8192): proj -> normalise -> logits -> top-k; bit-identical to the chain above.
+// mid-size batches (65..8192 rows) with projection and class head: two column-sliced launches (+ the top-k kernel) whose
+// results are bit-identical to the chunked sgemm -> l2norm -> sgemm path; emb_raw [n, E] and logits [n, C] are scratch / outputs
+bool score_mid_supported(int n, int D, int E, int C);
+cudaError_t launch_score_mid(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C, float scale,
+                             float* emb_raw, float* emb_out, float* logits, cudaStream_t stream);
 bool score_fused_supported(int n, int D, int E, int C);
 cudaError_t launch_score_fused(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C,
                                float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx,

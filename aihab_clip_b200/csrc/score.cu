@@ -3,9 +3,13 @@
 // (F.normalize -> 100. * f @ text_weights -> argmax), methods/utils.py:16-21 / aihab_utils/evaluation.py:261-273
 // (topk, sorted, lowest index first among exact ties).
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 #include <cuda_fp16.h>
 #include <math.h>
+
+#include <algorithm>
+#include <stdlib.h>
 
 namespace aihab {
 
@@ -408,6 +412,144 @@ __global__ void __launch_bounds__(256) score_fused_kernel(const float* __restric
   }
 }
 
+// ---- mid-size batches (one extraction batch of 65..8192 rows, e.g. the 256 rows of the headline step) ---------------
+// score_fused_kernel gives every CTA whole rows, so each of its n / 4 CTAs pulls ALL of visual.proj and the text matrix
+// (3.5 MB at 768 -> 512 -> 1000) through one SM's L2 port: 82-100 us for 256 rows whatever the row count.  These two
+// kernels slice the COLUMNS as well (16 rows x 32 embedding columns, 16 rows x 32 classes per CTA: 256 / 512 CTAs
+// at n = 256, 1000 classes), so an SM loads a 1/16 slice of the weights.  Per output the k loop is one ascending fmaf chain - the
+// order of sgemm_kernel - and the normalisation is l2norm_kernel's: results are bit-identical to the chunked path
+// (aihab_score for n > 8192) and do not depend on the batch composition.
+constexpr int MID_ROWS = 16;
+constexpr int MID_KC = 64;   // weight rows per shared-memory chunk (64 x 32 fp32 = 8 KB)
+constexpr int MID_NST = 4;   // chunk ring: MID_NST - 1 chunks in flight (the weights come from HBM once per step)
+
+// One thread's 4 columns of  sum over k (ascending, ONE fmaf chain per output) of a_row[k] * B[k][c0 + 4q .. + 3]  for the
+// CTA's 32-column slice of the row-major [K, ldb] matrix B.  The slice streams through a ring of MID_KC-row chunks in
+// shared memory (16-byte cp.async pieces, MID_NST - 1 chunks in flight), so no global-load latency sits inside the
+// dependent fmaf chain.  slice_issue / slice_dot are called by all 128 threads; one commit group per chunk index
+// (empty past the end) keeps the wait_group arithmetic uniform.
+struct Slice {
+  const float* B;
+  int K, ldb, ncols, c0;
+  float* sw;  // [MID_NST][MID_KC][32]
+};
+__device__ __forceinline__ void slice_issue(const Slice& sl, int ch, int tid) {
+  if (ch * MID_KC < sl.K) {
+    float* dst = sl.sw + (ch % MID_NST) * MID_KC * 32;
+    for (int i = tid; i < MID_KC * 8; i += 128) {
+      const int kk = i >> 3, qq = i & 7;
+      const int k = ch * MID_KC + kk, c = sl.c0 + 4 * qq;
+      const bool ok = k < sl.K && c < sl.ncols;
+      ptx::cp_async16(dst + kk * 32 + 4 * qq, ok ? sl.B + static_cast<size_t>(k) * sl.ldb + c : sl.B, ok);
+    }
+  }
+  ptx::cp_async_commit();
+}
+// chunks 0 .. MID_NST-2 must have been issued (in order, nothing issued after them)
+__device__ __forceinline__ float4 slice_dot(const Slice& sl, const float* a_row, int tid) {
+  const int q = tid & 7;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int nch = (sl.K + MID_KC - 1) / MID_KC;
+  for (int ch = 0; ch < nch; ++ch) {
+    slice_issue(sl, ch + MID_NST - 1, tid);  // into the slot consumed at iteration ch - 1 (all threads passed its barrier)
+    ptx::cp_async_wait<MID_NST - 1>();
+    __syncthreads();
+    const float* w = sl.sw + (ch % MID_NST) * MID_KC * 32 + 4 * q;
+    const float* a = a_row + ch * MID_KC;
+    const int kmax = min(MID_KC, sl.K - ch * MID_KC);
+    int kk = 0;
+    for (; kk + 8 <= kmax; kk += 8) {
+      // all shared-memory loads of 8 steps first (2 + 8 LDS.128), then the 32 fmaf: with two warps per scheduler
+      // nothing else hides the load-to-use latency inside the chain
+      const float4 f0 = *reinterpret_cast<const float4*>(a + kk), f1 = *reinterpret_cast<const float4*>(a + kk + 4);
+      const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+      float4 wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = *reinterpret_cast<const float4*>(w + (kk + j) * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc.x = fmaf(fv[j], wv[j].x, acc.x);
+        acc.y = fmaf(fv[j], wv[j].y, acc.y);
+        acc.z = fmaf(fv[j], wv[j].z, acc.z);
+        acc.w = fmaf(fv[j], wv[j].w, acc.w);
+      }
+    }
+    for (; kk < kmax; ++kk) {
+      const float f = a[kk];
+      const float4 w4 = *reinterpret_cast<const float4*>(w + kk * 32);
+      acc.x = fmaf(f, w4.x, acc.x);
+      acc.y = fmaf(f, w4.y, acc.y);
+      acc.z = fmaf(f, w4.z, acc.z);
+      acc.w = fmaf(f, w4.w, acc.w);
+    }
+    __syncthreads();
+  }
+  return acc;
+}
+
+// rows [row0, row0 + MID_ROWS) of a row-major [n, cols] fp32 matrix into shared memory (zero rows past n); cols % 4 == 0.
+// One commit group; the caller waits.
+__device__ __forceinline__ void rows_issue(float* dst, const float* __restrict__ src, int n, int cols, int row0, int tid) {
+  const int per_row = cols >> 2;
+  for (int i = tid; i < MID_ROWS * per_row; i += 128) {
+    const int r = i / per_row, c = (i - r * per_row) * 4;
+    const bool ok = row0 + r < n;
+    ptx::cp_async16(dst + r * cols + c, ok ? src + static_cast<size_t>(row0 + r) * cols + c : src, ok);
+  }
+  ptx::cp_async_commit();
+}
+
+__global__ void __launch_bounds__(128) score_proj_kernel(const float* __restrict__ feats, int n, int D,
+                                                         const float* __restrict__ proj, int E, float* __restrict__ emb_raw) {
+  extern __shared__ __align__(16) float sm[];  // [MID_ROWS][D] features | [MID_NST][MID_KC][32] weight chunks
+  ptx::griddep_launch();
+  ptx::griddep_wait();
+  const int row0 = blockIdx.y * MID_ROWS, c0 = blockIdx.x * 32;
+  const int tid = threadIdx.x;
+  const Slice sl{proj, D, E, E, c0, sm + MID_ROWS * D};
+  rows_issue(sm, feats, n, D, row0, tid);
+  for (int ch = 0; ch < MID_NST - 1; ++ch) slice_issue(sl, ch, tid);
+  const int r = tid >> 3, col = c0 + 4 * (tid & 7);
+  const float4 acc = slice_dot(sl, sm + r * D, tid);  // its first wait_group also covers the (older) row group
+  if (row0 + r < n) *reinterpret_cast<float4*>(emb_raw + static_cast<size_t>(row0 + r) * E + col) = acc;
+}
+
+__global__ void __launch_bounds__(128) score_logits_kernel(const float* __restrict__ emb_raw, int n, int E,
+                                                           const float* __restrict__ text_w, int C, float scale,
+                                                           float* __restrict__ emb_out, float* __restrict__ logits) {
+  extern __shared__ __align__(16) float sm[];  // [MID_ROWS][E] embeddings | [MID_NST][MID_KC][32] weight chunks
+  ptx::griddep_launch();
+  ptx::griddep_wait();
+  const int row0 = blockIdx.y * MID_ROWS, c0 = blockIdx.x * 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Slice sl{text_w, E, C, C, c0, sm + MID_ROWS * E};
+  rows_issue(sm, emb_raw, n, E, row0, tid);
+  for (int ch = 0; ch < MID_NST - 1; ++ch) slice_issue(sl, ch, tid);  // text-weight chunks fly during the normalisation
+  ptx::cp_async_wait<MID_NST - 1>();
+  __syncthreads();
+  // F.normalize (x / max(||x||, 1e-12)) with the summation order of l2norm_kernel; every column-slice CTA of a row
+  // group runs the same instructions on the same data, so they all hold the same normalised rows.  The rows stay in
+  // shared memory multiplied by `scale`: (100. * f) @ w puts the scale onto the features first (methods/utils.py:185)
+  for (int rr = 0; rr < MID_ROWS / 4; ++rr) {
+    float* row = sm + (warp * (MID_ROWS / 4) + rr) * E;
+    float s = 0.f;
+    for (int c = lane; c < E; c += 32) s = fmaf(row[c], row[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float denom = fmaxf(sqrtf(s), 1e-12f);
+    const int grow = row0 + warp * (MID_ROWS / 4) + rr;
+    for (int c = lane; c < E; c += 32) {
+      const float v = row[c] / denom;
+      row[c] = scale * v;
+      if (emb_out != nullptr && blockIdx.x == 0 && grow < n) emb_out[static_cast<size_t>(grow) * E + c] = v;
+    }
+  }
+  __syncthreads();
+  const int r = tid >> 3, col = c0 + 4 * (tid & 7);
+  const float4 acc = slice_dot(sl, sm + r * E, tid);
+  if (row0 + r < n && col < C) *reinterpret_cast<float4*>(logits + static_cast<size_t>(row0 + r) * C + col) = acc;
+}
+
 // ---- tensor-core scoring helpers (aihab_score16) -------------------------------------------------------------
 // 16-bit transpose: src [R, Cc] -> dst [Cc, R]   (visual.proj [D, E] -> [E, D], the K-major UMMA operand B)
 __global__ void transpose16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int R, int Cc) {
@@ -785,9 +927,54 @@ cudaError_t launch_l2norm_split(const float* emb, float* emb_out, void* a3, int 
   return cudaGetLastError();
 }
 
+bool score_mid_supported(int n, int D, int E, int C) {
+  static const bool enabled = [] {
+    const char* e = getenv("AIHAB_SCORE_MID");
+    return e == nullptr || e[0] != '0';
+  }();
+  // measured at n = 256, 768 -> 512: 1000 classes 68 us against 150 us for score_fused_kernel; 20 classes 54 against 44 us
+  // (both kernels are then bound by the per-CTA fmaf / shared-memory chain of the projection), so few-class heads stay
+  // on the one-launch kernel
+  return enabled && n > 64 && n <= 8192 && D > 0 && (D % 4) == 0 && (E % 32) == 0 && C > 64 && (C % 4) == 0 &&
+         static_cast<size_t>(MID_ROWS) * std::max(D, E) * sizeof(float) <= 96 * 1024;
+}
+
+cudaError_t launch_score_mid(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C, float scale,
+                             float* emb_raw, float* emb_out, float* logits, cudaStream_t stream) {
+  const size_t chunk = static_cast<size_t>(MID_NST) * MID_KC * 32 * sizeof(float);
+  const size_t smem_a = static_cast<size_t>(MID_ROWS) * D * sizeof(float) + chunk, smem_b = static_cast<size_t>(MID_ROWS) * E * sizeof(float) + chunk;
+  cudaError_t e;
+  if (smem_a > 48 * 1024 &&
+      (e = cudaFuncSetAttribute(score_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_a))) != cudaSuccess)
+    return e;
+  if (smem_b > 48 * 1024 &&
+      (e = cudaFuncSetAttribute(score_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_b))) != cudaSuccess)
+    return e;
+  const int row_groups = (n + MID_ROWS - 1) / MID_ROWS;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.stream = stream;
+  cfg.blockDim = dim3(128);
+  cfg.gridDim = dim3(E / 32, row_groups);
+  cfg.dynamicSmemBytes = smem_a;
+  if (proj == nullptr) emb_raw = const_cast<float*>(feats);  // features are already projected (E == D): normalise + logits only
+  else if ((e = cudaLaunchKernelEx(&cfg, score_proj_kernel, feats, n, D, proj, E, emb_raw)) != cudaSuccess) return e;
+  cfg.gridDim = dim3((C + 31) / 32, row_groups);
+  cfg.dynamicSmemBytes = smem_b;
+  return cudaLaunchKernelEx(&cfg, score_logits_kernel, static_cast<const float*>(emb_raw), n, E, text_w, C, scale, emb_out, logits);
+}
+
 bool score_fused_supported(int n, int D, int E, int C) {
   const size_t smem = static_cast<size_t>(RPB) * (D + 2 * E + (C > 0 ? C : 0)) * sizeof(float);
-  return n <= 8192 && smem <= 160 * 1024 && (E % 4) == 0 && (D % 2) == 0;
+  static const int max_rows = [] {
+    const char* e = getenv("AIHAB_SCORE_FUSED_MAX_ROWS");
+    return e ? atoi(e) : 8192;
+  }();
+  return n <= max_rows && smem <= 160 * 1024 && (E % 4) == 0 && (D % 2) == 0;
 }
 
 cudaError_t launch_score_fused(const float* feats, int n, int D, const float* proj, int E, const float* text_w, int C,

@@ -208,6 +208,29 @@ def test_score_matches_oracle(cuda_device, n, D, E, Cn, k):
     np.testing.assert_array_equal(val.cpu().numpy(), np.take_along_axis(logits.cpu().numpy(), idx.cpu().numpy(), 1))
 
 
+def test_score_mid_path_equals_the_chunked_path_bit_for_bit(cuda_device):
+    """65..8192 rows take the column-sliced kernels (score_proj_kernel / score_logits_kernel), more rows the chunked
+    sgemm -> l2norm -> sgemm path: the same ascending fmaf chains and the same normalisation, so a row's embedding,
+    logits and top-k must not depend on which path (or which batch) it went through."""
+    _lib, ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for (D, E, Cn, k) in ((768, 512, 1000, 5), (256, 128, 260, 3)):
+        feats = torch.randn(9000, D, generator=g).to(cuda_device)
+        proj = (torch.randn(D, E, generator=g) * D ** -0.5).to(cuda_device)
+        tw = torch.nn.functional.normalize(torch.randn(Cn, E, generator=g), dim=1).t().contiguous().to(cuda_device)
+        emb_c, lg_c, idx_c, val_c = ops.score(feats, proj, tw, 100.0, k)                 # chunked (n > 8192)
+        for n in (300, 77, 8192):
+            emb_m, lg_m, idx_m, val_m = ops.score(feats[:n].contiguous(), proj, tw, 100.0, k)   # mid path
+            assert torch.equal(emb_m, emb_c[:n]) and torch.equal(lg_m, lg_c[:n])
+            assert torch.equal(idx_m, idx_c[:n]) and torch.equal(val_m, val_c[:n])
+            _, _, idx_n, _ = ops.score(feats[:n].contiguous(), proj, tw, 100.0, k, want_emb=False, want_logits=False)
+            assert torch.equal(idx_n, idx_c[:n])                                         # scratch logits, same result
+        # already projected features (proj = None, the call of the extraction step): normalise + logits + top-k only
+        e_c, l_c, i_c, _ = ops.score(emb_c * 3.0, None, tw, 100.0, k)
+        e_m, l_m, i_m, _ = ops.score((emb_c * 3.0)[:256].contiguous(), None, tw, 100.0, k)
+        assert torch.equal(e_m, e_c[:256]) and torch.equal(l_m, l_c[:256]) and torch.equal(i_m, i_c[:256])
+
+
 def test_topk_exact_ties(cuda_device):
     _lib, ops = _ops()
     lg = np.zeros((4, 8), dtype=np.float32)
