@@ -324,19 +324,14 @@ __global__ void __launch_bounds__(256) normalize_im2col16_kernel(const uint8_t* 
       strip[i] = __ldg(src0 + r * row_pitch + (i - r * RC));
     }
   }
-  // (x / 255 - mean) / std has 256 x 3 possible results: a shared-memory table of the 16-bit outputs (computed with
-  // the exact arithmetic of normalize_u8) replaces ~10 FP instructions per byte by one 16-bit shared-memory load
-  __shared__ uint16_t lut[3][256];
-  {
-    const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
-    const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
-    const float rstd[3] = {1.0f / 0.26862954f, 1.0f / 0.26130258f, 1.0f / 0.27577711f};
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
-      const int c = i >> 8;
-      lut[c][i & 255] = static_cast<uint16_t>(ptx::pack2<BF16>(normalize_u8(i & 255, mean[c], stdv[c], rstd[c]), 0.f) & 0xffffu);
-    }
-  }
+  // (x / 255 - mean) / std, rounded to 16 bits, has 256 x 3 possible results, and ONE fp32 fma reproduces every one of
+  // them: round16(fma(x, A_c, C_c)) with A_c = RN(1 / (255 std_c)), C_c = RN(-mean_c / std_c) equals the 16-bit rounding
+  // of the reference's divide / subtract / divide chain (normalize_u8) for all 768 inputs, fp16 and bf16 (checked
+  // exhaustively on the host, and by the bit-exact preprocessing tests).  A byte becomes a float without a conversion
+  // instruction: PRMT builds 0x4B0000xx = 8388608 + x, one FADD removes the offset.
   __syncthreads();
+  constexpr float kA[3] = {0.014598426f, 0.015007768f, 0.014220066f};
+  constexpr float kC[3] = {-1.7922626f, -1.7520971f, -1.4802198f};
   const int kx8n = p >> 3;              // 8-pixel groups per patch row
   const int groups = g * p * kx8n;      // 8-pixel groups of the strip
   uint16_t* dst0 = out + (static_cast<size_t>(img) * g + gy) * g * 3 * p * p;
@@ -353,13 +348,15 @@ __global__ void __launch_bounds__(256) normalize_im2col16_kernel(const uint8_t* 
       w[2 * i] = v.x;
       w[2 * i + 1] = v.y;
     }
-    auto byte_at = [&](int i) { return (w[i >> 2] >> ((i & 3) * 8)) & 0xffu; };
+    auto val_at = [&](int i, int c) {  // normalised value of byte i of the 24 (channel c = i % 3)
+      const uint32_t bits = __byte_perm(w[i >> 2], 0x4B000000u, 0x7440u | static_cast<uint32_t>(i & 3));
+      return fmaf(__uint_as_float(bits) - 8388608.0f, kA[c], kC[c]);
+    };
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       uint32_t pk[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        pk[j] = static_cast<uint32_t>(lut[c][byte_at(6 * j + c)]) | (static_cast<uint32_t>(lut[c][byte_at(6 * j + 3 + c)]) << 16);
+      for (int j = 0; j < 4; ++j) pk[j] = ptx::pack2<BF16>(val_at(6 * j + c, c), val_at(6 * j + 3 + c, c));
       *reinterpret_cast<uint4*>(dst0 + (gx * 3 + c) * p * p + ky * p + kx8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
