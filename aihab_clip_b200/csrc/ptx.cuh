@@ -310,6 +310,14 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_wait_regs16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // griddep_launch: lets the next kernel of the stream (launched with programmatic stream serialization) be scheduled
 // while this grid still runs; griddep_wait: blocks until the previous grid has completed and its memory is visible.
