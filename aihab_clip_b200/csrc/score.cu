@@ -276,6 +276,22 @@ __global__ void __launch_bounds__(256) score_fused_kernel(const float* __restric
   __shared__ float s_den[RPB];
   const int row0 = blockIdx.x * RPB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Warm L2 first: in the extraction step visual.proj and the text matrix were evicted by the ~26 GB the tower moved since
+  // the last call, and all CTAs walk them in lockstep through dependent 8-load batches - a cold miss would be paid ~50
+  // times in a row by every CTA.  One 128-byte line per thread across the grid instead: one HBM round trip in total.
+  {
+    const size_t gtid = static_cast<size_t>(blockIdx.x) * 256 + tid, gstride = static_cast<size_t>(gridDim.x) * 256;
+    if (proj != nullptr) {
+      const size_t lines = (static_cast<size_t>(D) * E * sizeof(float) + 127) / 128;
+      for (size_t i = gtid; i < lines; i += gstride)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(proj) + i * 128));
+    }
+    if (text_w != nullptr) {
+      const size_t lines = (static_cast<size_t>(E) * C * sizeof(float) + 127) / 128;
+      for (size_t i = gtid; i < lines; i += gstride)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(text_w) + i * 128));
+    }
+  }
   for (int i = tid; i < RPB * D; i += 256) {
     const int r = i / D;
     sf[i] = (row0 + r < n) ? feats[static_cast<size_t>(row0 + r) * D + (i - r * D)] : 0.f;
@@ -289,12 +305,14 @@ __global__ void __launch_bounds__(256) score_fused_kernel(const float* __restric
 #pragma unroll
       for (int r = 0; r < RPB; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
       int kk = k0;
-      for (; kk + 8 <= k1; kk += 8) {
-        float4 w[8];
+      // PU weight rows in flight per thread: the CTA is one dependent chain of D / 2 / PU round trips to L2
+      constexpr int PU = 16;
+      for (; kk + PU <= k1; kk += PU) {
+        float4 w[PU];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(proj + static_cast<size_t>(kk + j) * E + e0));
+        for (int j = 0; j < PU; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(proj + static_cast<size_t>(kk + j) * E + e0));
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < PU; ++j)
 #pragma unroll
           for (int r = 0; r < RPB; ++r) {
             const float f = sf[r * D + kk + j];
