@@ -14,7 +14,8 @@ if grep -q "passed" gpurun_out/fused/test_dbg.log && ! grep -q failed gpurun_out
   run fused AIHAB_MLP_FUSED=1 AIHAB_MLP_RING_PAIRS=40
   run nowait AIHAB_MLP_FUSED=1 AIHAB_MLP_RING_PAIRS=40 AIHAB_MLP_NOWAIT=1
   run lag5 AIHAB_MLP_FUSED=1 AIHAB_MLP_RING_PAIRS=48 AIHAB_MLP_LAG=5
-  run s3r4 AIHAB_MLP_FUSED=1 AIHAB_MLP_RING_PAIRS=40 AIHAB_CLIP_LIB=$PWD/ab/lib_s3r4.so
+  # 3 operand stages + 4-box rings: bash tools/build_variant.sh s3r4 -DAIHAB_FUSED_STAGES=3 -DAIHAB_FUSED_RING=4
+  [ -f ab/lib_s3r4.so ] && run s3r4 AIHAB_MLP_FUSED=1 AIHAB_MLP_RING_PAIRS=40 AIHAB_CLIP_LIB=$PWD/ab/lib_s3r4.so
   run base2 AIHAB_MLP_FUSED=0
 fi
 cat gpurun_out/fused/summary.txt
