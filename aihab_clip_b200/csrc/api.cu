@@ -1261,7 +1261,7 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
   CK(projT_t.alloc(static_cast<size_t>(E) * D * 2));
   CK(w3_t.alloc(static_cast<size_t>(C) * 3 * E * 2));
   CK(a3_t.alloc(static_cast<size_t>(rows_tmp) * 3 * E * 2));
-  CK(emb_raw_t.alloc(static_cast<size_t>(rows_tmp) * E * 4));
+  // (allocated below only if the fp32 embeddings are materialised)
   // k <= 8 and no logits requested: the logits GEMM keeps per-row top-k candidates in its epilogue (EPI_TOPK_32) and the
   // [rows, C] logits never reach HBM; AIHAB_SCORE16_FUSED=0 restores the store + top-k kernel pair (A/B, tests)
   static const bool fused_env = [] {
@@ -1279,6 +1279,17 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
   } else if (logits_out == nullptr) {
     CK(logit_t.alloc(static_cast<size_t>(rows_tmp) * C * 4));
   }
+  // no embeddings requested: GEMM 1 writes the hi | hi | lo split of the RAW embedding rows and their chunk sums of
+  // squares itself (EPI_SPLIT3_16) and the logits GEMM normalises its accumulator rows - the fp32 embeddings and the
+  // normalise + split pass over them disappear (AIHAB_SCORE16_SPLIT=0: the three-kernel sequence)
+  static const bool split_env = [] {
+    const char* e = getenv("AIHAB_SCORE16_SPLIT");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool split = split_env && emb_out == nullptr && (E % 64) == 0;
+  AsyncTemp<float> ss_t(s);
+  if (split) CK(ss_t.alloc(static_cast<size_t>(rows_tmp) * (E / 64) * 4));
+  else CK(emb_raw_t.alloc(static_cast<size_t>(rows_tmp) * E * 4));
   void *projT = projT_t.p, *w3 = w3_t.p, *a3 = a3_t.p;
   float *emb_raw = emb_raw_t.p, *logit_tmp = logit_t.p;
   ProfScope ps(PC_SCORE, 2.0 * n * (static_cast<double>(D) * E + static_cast<double>(E) * C), s);
@@ -1298,12 +1309,26 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
     p.N = E;
     p.K = D;
     p.ab_format = bf16;
-    p.epilogue = aihab::EPI_SCALE_32;
-    p.out32 = emb_raw;
-    p.ldo = E;
     p.scale = 1.0f;
-    CKL(aihab::launch_gemm(ma, mw, nullptr, p, bn, sms, s));
-    CKL(aihab::launch_l2norm_split(emb_raw, emb_out ? emb_out + static_cast<size_t>(i0) * E : nullptr, a3, nb, E, s));
+    p.row_ss = nullptr;
+    if (split) {
+      p.epilogue = aihab::EPI_SPLIT3_16;
+      p.out16 = a3;
+      p.out32 = nullptr;
+      p.ldo = 3 * E;
+      p.stats_out = ss_t.p;
+      CKL(aihab::launch_gemm(ma, mw, nullptr, p, bn, sms, s));
+      p.out16 = nullptr;
+      p.stats_out = nullptr;
+      p.row_ss = ss_t.p;
+      p.row_ss_n = E / 64;
+    } else {
+      p.epilogue = aihab::EPI_SCALE_32;
+      p.out32 = emb_raw;
+      p.ldo = E;
+      CKL(aihab::launch_gemm(ma, mw, nullptr, p, bn, sms, s));
+      CKL(aihab::launch_l2norm_split(emb_raw, emb_out ? emb_out + static_cast<size_t>(i0) * E : nullptr, a3, nb, E, s));
+    }
     // logits = scale * (e_hi w_hi + e_hi w_lo + e_lo w_hi): one K = 3E fp16 GEMM (methods/utils.py:185)
     float* lg = logits_out ? logits_out + static_cast<size_t>(i0) * C : logit_tmp;
     bn = fused ? bn_logits : aihab::gemm_block_n(nb, C, sms);
@@ -1315,6 +1340,7 @@ int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj
     p.out32 = fused ? nullptr : lg;
     p.ldo = C;
     p.scale = scale;
+    p.epilogue = aihab::EPI_SCALE_32;
     if (fused) {
       p.epilogue = aihab::EPI_TOPK_32;
       p.topk_k = k;

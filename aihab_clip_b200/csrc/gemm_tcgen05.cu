@@ -108,7 +108,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr int kStages = L::kStages;
   constexpr bool kLn = (EPI == EPI_LN_BIAS_16 || EPI == EPI_LN_BIAS_GELU_16);
   constexpr bool kGelu = (EPI == EPI_BIAS_GELU_16 || EPI == EPI_LN_BIAS_GELU_16);
-  constexpr bool kOut16 = (EPI == EPI_BIAS_16 || EPI == EPI_BIAS_GELU_16 || kLn);
+  constexpr bool kSplit3 = (EPI == EPI_SPLIT3_16);
+  constexpr bool kOut16 = (EPI == EPI_BIAS_16 || EPI == EPI_BIAS_GELU_16 || kLn || kSplit3);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024 B aligned, still a __shared__ pointer
@@ -368,6 +369,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
 
+      // EPI_SCALE_32 / EPI_TOPK_32 behind an EPI_SPLIT3_16 producer: F.normalize of the A rows applied to the accumulator
+      // row instead (scale / max(||row||, 1e-12)); the chunk sums are added in ascending order
+      [[maybe_unused]] float sc = p.scale;
+      if constexpr (EPI == EPI_SCALE_32 || EPI == EPI_TOPK_32) {
+        if (p.row_ss != nullptr) {
+          const int grow = m0 + lane;
+          float ssum = 0.f;
+          if (grow < p.M)
+            for (int b = 0; b < p.row_ss_n; ++b) ssum += __ldg(p.row_ss + static_cast<size_t>(grow) * p.row_ss_n + b);
+          sc = p.scale / fmaxf(sqrtf(ssum), 1e-12f);
+        }
+      }
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
       if constexpr (TWO && EPI == EPI_BIAS_RES_32) {
@@ -414,6 +427,59 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           const float* cb = sb + c * 64;
           const float* cx = sx + c * 64;
+          if constexpr (kSplit3) {
+            // hi / lo split of the chunk, its sum of squares, three stores (hi | hi | lo) through the one staging tile
+            uint32_t pk[32];
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v0 = __uint_as_float(j < 16 ? ra[2 * j] : rb[2 * j - 32]) + cb[2 * j];
+              const float v1 = __uint_as_float(j < 16 ? ra[2 * j + 1] : rb[2 * j - 31]) + cb[2 * j + 1];
+              ss = fmaf(v0, v0, ss);
+              ss = fmaf(v1, v1, ss);
+              pk[j] = ptx::pack2<false>(v0, v1);
+              // keep the residuals in the accumulator registers for the second pass
+              const __half2 h2 = *reinterpret_cast<const __half2*>(&pk[j]);
+              const float l0 = v0 - __low2float(h2), l1 = v1 - __high2float(h2);
+              if (j < 16) {
+                ra[2 * j] = __float_as_uint(l0);
+                ra[2 * j + 1] = __float_as_uint(l1);
+              } else {
+                rb[2 * j - 32] = __float_as_uint(l0);
+                rb[2 * j - 31] = __float_as_uint(l1);
+              }
+            }
+            const int grow = m0 + lane;
+            if (grow < p.M && n0 + c * 64 < p.N) p.stats_out[static_cast<size_t>(grow) * ((p.N + 63) / 64) + (n0 / 64 + c)] = ss;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+              if (pass == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  pk[j] = ptx::pack2<false>(__uint_as_float(j < 16 ? ra[2 * j] : rb[2 * j - 32]),
+                                            __uint_as_float(j < 16 ? ra[2 * j + 1] : rb[2 * j - 31]));
+              }
+              if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store of this warp has finished reading the tile
+              __syncwarp();
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) =
+                    make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+              }
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                if (pass == 0) {
+                  ptx::tma_store_2d(&tmap_c, stg, n0 + c * 64, st_row);
+                  ptx::tma_store_2d(&tmap_c, stg, p.N + n0 + c * 64, st_row);
+                } else {
+                  ptx::tma_store_2d(&tmap_c, stg, 2 * p.N + n0 + c * 64, st_row);
+                }
+                ptx::bulk_commit();
+              }
+            }
+            continue;
+          }
           uint32_t pk[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -567,7 +633,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int col = col0 + j;
-              const float v = col < p.N ? fmaf(__uint_as_float(r[j]), p.scale, sb[c * 32 + j]) : -INFINITY;
+              const float v = col < p.N ? fmaf(__uint_as_float(r[j]), sc, sb[c * 32 + j]) : -INFINITY;
 #pragma unroll
               for (int i = S - 1; i >= 1; --i) {
                 const bool ci = v > tv[i], cm = v > tv[i - 1];
@@ -614,10 +680,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               v.z += sb[c * 32 + 4 * u + 2];
               v.w += sb[c * 32 + 4 * u + 3];
             } else if constexpr (EPI == EPI_SCALE_32) {
-              v.x = fmaf(v.x, p.scale, sb[c * 32 + 4 * u]);
-              v.y = fmaf(v.y, p.scale, sb[c * 32 + 4 * u + 1]);
-              v.z = fmaf(v.z, p.scale, sb[c * 32 + 4 * u + 2]);
-              v.w = fmaf(v.w, p.scale, sb[c * 32 + 4 * u + 3]);
+              v.x = fmaf(v.x, sc, sb[c * 32 + 4 * u]);
+              v.y = fmaf(v.y, sc, sb[c * 32 + 4 * u + 1]);
+              v.z = fmaf(v.z, sc, sb[c * 32 + 4 * u + 2]);
+              v.w = fmaf(v.w, sc, sb[c * 32 + 4 * u + 3]);
             }
             *reinterpret_cast<float4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = v;
           }
@@ -1161,6 +1227,7 @@ cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, const CUtens
       return launch_one<BN, EPI_BIAS_RES_32>(ta, tw, tc, p, grid, pair, stream);
     case EPI_PATCH_32: return launch_one<BN, EPI_PATCH_32>(ta, tw, tc, p, grid, pair, stream);
     case EPI_SCALE_32: return launch_one<BN, EPI_SCALE_32>(ta, tw, tc, p, grid, pair, stream);
+    case EPI_SPLIT3_16: return launch_one<BN, EPI_SPLIT3_16>(ta, tw, tc, p, grid, pair, stream);
     case EPI_LN_BIAS_16: return launch_one<BN, EPI_LN_BIAS_16>(ta, tw, tc, p, grid, pair, stream);
     case EPI_LN_BIAS_GELU_16: return launch_one<BN, EPI_LN_BIAS_GELU_16>(ta, tw, tc, p, grid, pair, stream);
     case EPI_TOPK_32:
@@ -1189,7 +1256,7 @@ cudaError_t gemm_init() {
   AIHAB_SET(256, EPI_LN_BIAS_GELU_16) AIHAB_SET(128, EPI_LN_BIAS_16) AIHAB_SET(128, EPI_LN_BIAS_GELU_16)
   AIHAB_SET(128, EPI_BIAS_16) AIHAB_SET(128, EPI_BIAS_GELU_16) AIHAB_SET(128, EPI_BIAS_RES_32)
   AIHAB_SET(128, EPI_PATCH_32) AIHAB_SET(128, EPI_SCALE_32) AIHAB_SET(256, EPI_TOPK_32) AIHAB_SET(128, EPI_TOPK_32)
-  AIHAB_SET(256, EPI_TOPK5) AIHAB_SET(128, EPI_TOPK5)
+  AIHAB_SET(256, EPI_TOPK5) AIHAB_SET(128, EPI_TOPK5) AIHAB_SET(256, EPI_SPLIT3_16) AIHAB_SET(128, EPI_SPLIT3_16)
 #undef AIHAB_SET
   if ((e = cudaFuncSetAttribute(gemm_kernel<256, EPI_RES_WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 SmemLayout<256, EPI_RES_WIDE, true>::kDynamic)) != cudaSuccess)
@@ -1365,7 +1432,10 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, co
       return cudaErrorInvalidValue;
   }
   const bool ln = (p.epilogue == EPI_LN_BIAS_16 || p.epilogue == EPI_LN_BIAS_GELU_16);
-  const bool out16 = (p.epilogue == EPI_BIAS_16 || p.epilogue == EPI_BIAS_GELU_16 || ln);
+  const bool split3 = p.epilogue == EPI_SPLIT3_16;
+  const bool out16 = (p.epilogue == EPI_BIAS_16 || p.epilogue == EPI_BIAS_GELU_16 || ln || split3);
+  if (split3 && (p.stats_out == nullptr || p.ldo != 3 * p.N || (p.N & 63) || p.ring_mode != 0)) return cudaErrorInvalidValue;
+  if (p.row_ss != nullptr && p.row_ss_n <= 0) return cudaErrorInvalidValue;
   if (ln && (p.ln_stats == nullptr || p.ln_s == nullptr || p.ln_nsb <= 0 || p.bias == nullptr)) return cudaErrorInvalidValue;
   if (p.epilogue == EPI_BIAS_RES_32 && p.ln_gamma != nullptr && (p.a16_out == nullptr || p.stats_out == nullptr))
     return cudaErrorInvalidValue;
@@ -1378,7 +1448,7 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, co
   CUtensorMap out_map;
   if (out16 && tmap_c == nullptr) {  // the 16-bit epilogues store through TMA: 64-column x 32-row boxes over out16
     if (reinterpret_cast<uintptr_t>(p.out16) & 15) return cudaErrorInvalidValue;
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.N), static_cast<cuuint64_t>(p.ring_mode == 1 ? p.ring_rows : p.M)};
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(split3 ? 3 * p.N : p.N), static_cast<cuuint64_t>(p.ring_mode == 1 ? p.ring_rows : p.M)};
     cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p.ldo) * 2};
     cuuint32_t box[2] = {64, 32};
     cuuint32_t estr[2] = {1, 1};

@@ -42,6 +42,11 @@ enum GemmEpilogue : int {
   // cand_val / cand_idx [M, 2 * n_tiles, TOPK_SLOTS]; a merge pass picks the row's final top-k.  The logits of the
   // scoring path never reach HBM (methods/utils.py:16-21,185-186).
   EPI_TOPK_32 = 7,
+  // out16 = [M, 3N] fp16 rows (hi | hi | lo) of acc (+ bias): hi = fp16(v), lo = fp16(v - hi) - the A operand of the exact
+  // three-term logits GEMM of aihab_score16 (W' = w_hi | w_lo | w_hi) - and stats_out[m, n / 64] = sum of v^2 over the
+  // 64-column chunk.  The rows are NOT normalised: the consumer GEMM scales its accumulator rows by
+  // 1 / max(sqrt(sum of the chunks), 1e-12) (GemmParams.row_ss), which is F.normalize applied after the product.
+  EPI_SPLIT3_16 = 8,
 };
 constexpr int TOPK_SLOTS = 8;  // candidates kept per (row, epilogue warp) in EPI_TOPK_32; k <= TOPK_SLOTS
 
@@ -72,6 +77,10 @@ struct GemmParams {
   // EPI_TOPK_32: candidate buffers [M, 2 * ceil(N / BN), TOPK_SLOTS]
   float* cand_val;
   int* cand_idx;
+  // EPI_SCALE_32 / EPI_TOPK_32 (optional): per-row chunk sums of squares [M, row_ss_n] from an EPI_SPLIT3_16 producer; the
+  // epilogue multiplies `scale` by 1 / max(sqrt(sum), 1e-12) of its row
+  const float* row_ss;
+  int row_ss_n;
   int topk_k;  // the k the caller needs (1..TOPK_SLOTS; 0 = TOPK_SLOTS): k <= 5 keeps 5 candidates per slot group
   // Pipelined GEMM pair through an L2-resident ring (CTA pairs only; c_fc -> c_proj): the PRODUCER GEMM (ring_mode 1,
   // 16-bit epilogue) stores its output rows modulo ring_rows, counts every finished epilogue warp of a 256-row pair-row in

@@ -272,6 +272,17 @@ def test_score16_tensor_core_path(cuda_device, dtype, n, D, E, Cn, k):
     _, l32, i32, _ = ops.score(feats.to(cuda_device).float(), proj.to(cuda_device).float(),
                                torch.from_numpy(tw).to(cuda_device), 100.0, k)
     np.testing.assert_allclose(logits.cpu().numpy(), l32.cpu().numpy(), atol=5e-4, rtol=0)
+    # without the embeddings the first GEMM writes the hi | hi | lo split of the RAW rows itself (EPI_SPLIT3_16) and the
+    # logits GEMM normalises its accumulator rows: same gates against fp64, with and without the logits in HBM
+    _, lg2, idx2, val2 = ops.score16(feats.to(cuda_device), proj.to(cuda_device), torch.from_numpy(tw).to(cuda_device),
+                                     100.0, k, want_emb=False, want_logits=True)
+    np.testing.assert_allclose(lg2.cpu().numpy(), l64, atol=3e-4, rtol=0)
+    np.testing.assert_array_equal(idx2.cpu().numpy(), O.topk_indices(lg2.cpu().numpy(), k))
+    np.testing.assert_array_equal(idx2.cpu().numpy()[untied], O.topk_indices(l64, k)[untied])
+    if k <= 8:
+        _, _, idx3, val3 = ops.score16(feats.to(cuda_device), proj.to(cuda_device), torch.from_numpy(tw).to(cuda_device),
+                                       100.0, k)
+        assert torch.equal(idx3, idx2) and torch.equal(val3, val2)        # top-k in the GEMM epilogue, same arithmetic
 
 
 @pytest.mark.parametrize("n,C3,C2,k", [(257, 20, 11, 3), (5, 20, 11, 1), (4097, 37, 5, 5), (64, 1000, 100, 5)])
