@@ -181,8 +181,10 @@ AIHAB_API int aihab_l2_normalize(const void* x, int in_dtype, int rows, int cols
  *   text_w  : [E, C] fp32, C % 4 == 0
  * feats16 @ proj16 runs as a tcgen05 GEMM with fp32 accumulation: products of 16-bit values are exact in fp32, so
  * the result differs from the fp32 reference only by summation order.  The logits GEMM multiplies fp16 hi/lo splits
- * of the normalised embedding and of the text weights (e_hi w_hi + e_hi w_lo + e_lo w_hi, relative error ~2^-21),
- * i.e. top-k indices equal the fp32 reference's wherever its scores are untied.  Outputs as in aihab_score. */
+ * of the embedding and of the text weights (e_hi w_hi + e_hi w_lo + e_lo w_hi, relative error ~2^-21): of the
+ * NORMALISED embedding when emb_out is requested, else of the raw one with F.normalize applied to the accumulator row
+ * (scale / max(||e||, 1e-12)) - the same value up to fp32 rounding.  Top-k indices equal the fp32 reference's
+ * wherever its scores are untied.  Outputs as in aihab_score. */
 AIHAB_API int aihab_score16(const void* feats16, int n, int D, int dtype, const void* proj16, int E, const float* text_w,
                             int C, float scale, int k, float* emb_out, float* logits_out, int64_t* topk_idx,
                             float* topk_val, void* stream);
