@@ -152,7 +152,9 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* dst, const 
 //   pass 1: a thread's tap window (<= KMAX pixels = 36 bytes) is loaded as ten aligned words and re-aligned with funnel
 //           shifts (its byte offset is the same for every row of the strip); the result goes to a CHANNEL-PLANAR tile;
 //   pass 2: a thread produces four consecutive pixels of one channel: one word per tap from the planar tile.
-template <typename OutT>
+// KT = tap capacity of the horizontal pass (4 / 6 / 9 / KMAX, the smallest that holds the filter): the unrolled tap
+// loop issues its predicated-off taps too, so a 9-tap filter (439 -> 224) in a 12-tap loop wastes a quarter of it
+template <typename OutT, int KT>
 __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ in_end,
                                                                 int sh, int sw, int R, ResampleTables t, OutT* __restrict__ out,
                                                                 int layout, int p, int Kpad, int in_cap, int rows_cap) {
@@ -194,44 +196,50 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* _
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
     const uint8_t* gp = a0 + (static_cast<size_t>(i) << 4);
     if (gp >= in && gp + 16 <= in_end) {
-      reinterpret_cast<uint4*>(sin)[i] = __ldg(reinterpret_cast<const uint4*>(gp));
+      // cp.async: the ~13 vectors of a thread are all in flight at once (a load -> store loop pays the HBM latency per
+      // vector: it was 23 % of the kernel's stall samples)
+      ptx::cp_async16(sin + (static_cast<size_t>(i) << 4), gp, true);
     } else {  // first / last vector of the whole batch buffer
       for (int b = 0; b < 16; ++b) sin[(i << 4) + b] = (gp + b >= in && gp + b < in_end) ? __ldg(gp + b) : 0;
     }
   }
+  ptx::cp_async_commit();
+  ptx::cp_async_wait<0>();
   __syncthreads();
   // ---- pass 1: horizontal
+  const uint32_t sin_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(sin));
   for (int ox = threadIdx.x; ox < R; ox += blockDim.x) {
     const int rx = t.crop_left + ox;
     int xmin = rx, cnt = 1;
-    int k[KMAX];
+    int k[KT];
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j) k[j] = 0;
+    for (int j = 0; j < KT; ++j) k[j] = 0;
     k[0] = 1 << 22;  // no horizontal resize: the pixel itself (4194304 * v + 2^21) >> 22 == v
     if (t.need_h) {
       xmin = t.h_bounds[2 * rx];
       cnt = t.h_bounds[2 * rx + 1];
 #pragma unroll
-      for (int j = 0; j < KMAX; ++j) k[j] = j < cnt ? __ldg(t.h_coeffs + static_cast<size_t>(rx) * t.h_ksize + j) : 0;
+      for (int j = 0; j < KT; ++j) k[j] = j < cnt ? __ldg(t.h_coeffs + static_cast<size_t>(rx) * t.h_ksize + j) : 0;
     }
-    const int nw = (3 * cnt + 3) >> 2;        // words of window bytes after re-alignment
     for (int r = 0; r < nrows; ++r) {
       const int off = head + r * row_bytes + xmin * 3;
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(sin + (off & ~3));
+      const uint32_t wa = sin_u32 + static_cast<uint32_t>(off & ~3);
       const int sh8 = (off & 3) * 8;
-      uint32_t w[KMAX * 3 / 4 + 1];
+      constexpr int NW = (KT * 3 + 3) / 4;  // words that hold KT pixels
+      uint32_t w[NW + 1];
+      // unconditional loads through explicit shared-space addresses: words past the window only meet k[j] = 0 (the
+      // staging buffer has 48 B of slack), and the compiler no longer re-derives the shared window per predicated load
 #pragma unroll
-      for (int i = 0; i < KMAX * 3 / 4 + 1; ++i) w[i] = i <= nw ? wp[i] : 0u;
+      for (int i = 0; i < NW + 1; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(wa + 4u * i));
 #pragma unroll
-      for (int i = 0; i < KMAX * 3 / 4; ++i) w[i] = __funnelshift_r(w[i], w[i + 1], sh8);  // window byte b = byte b of w[]
+      for (int i = 0; i < NW; ++i) w[i] = __funnelshift_r(w[i], w[i + 1], sh8);  // window byte b = byte b of w[]
       int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+      // taps past cnt carry k[j] = 0 and bytes of the zero-filled / neighbouring words: no predicate, one PRMT per byte
 #pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        if (j < cnt) {
-          s0 += static_cast<int>((w[(3 * j) >> 2] >> (((3 * j) & 3) * 8)) & 0xffu) * k[j];
-          s1 += static_cast<int>((w[(3 * j + 1) >> 2] >> (((3 * j + 1) & 3) * 8)) & 0xffu) * k[j];
-          s2 += static_cast<int>((w[(3 * j + 2) >> 2] >> (((3 * j + 2) & 3) * 8)) & 0xffu) * k[j];
-        }
+      for (int j = 0; j < KT; ++j) {
+        s0 += static_cast<int>(__byte_perm(w[(3 * j) >> 2], 0u, 0x4440u | ((3 * j) & 3))) * k[j];
+        s1 += static_cast<int>(__byte_perm(w[(3 * j + 1) >> 2], 0u, 0x4440u | ((3 * j + 1) & 3))) * k[j];
+        s2 += static_cast<int>(__byte_perm(w[(3 * j + 2) >> 2], 0u, 0x4440u | ((3 * j + 2) & 3))) * k[j];
       }
       uint8_t* o = tile + r * R + ox;
       o[0] = static_cast<uint8_t>(clip8(s0));
@@ -256,10 +264,10 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* _
       for (int j = 0; j < cnt; ++j) {
         const int kj = __ldg(kk + j);
         const uint32_t w = *reinterpret_cast<const uint32_t*>(col + (ymin + j) * R);
-        s[0] += static_cast<int>(w & 0xffu) * kj;
-        s[1] += static_cast<int>((w >> 8) & 0xffu) * kj;
-        s[2] += static_cast<int>((w >> 16) & 0xffu) * kj;
-        s[3] += static_cast<int>(w >> 24) * kj;
+        s[0] += static_cast<int>(__byte_perm(w, 0u, 0x4440u)) * kj;
+        s[1] += static_cast<int>(__byte_perm(w, 0u, 0x4441u)) * kj;
+        s[2] += static_cast<int>(__byte_perm(w, 0u, 0x4442u)) * kj;
+        s[3] += static_cast<int>(__byte_perm(w, 0u, 0x4443u)) * kj;
       }
     } else {
       const uint32_t w = *reinterpret_cast<const uint32_t*>(col + oy * R);
@@ -320,7 +328,9 @@ __global__ void __launch_bounds__(256) normalize_im2col16_kernel(const uint8_t* 
     // one warp per strip row, lanes over its 16-byte vectors: no division, every row a contiguous run
     for (int r = threadIdx.x >> 5; r < p; r += 8)
       for (int v = threadIdx.x & 31; v < vec_per_row; v += 32)
-        reinterpret_cast<uint4*>(strip + r * RC)[v] = __ldg(reinterpret_cast<const uint4*>(src0 + r * row_pitch) + v);
+        ptx::cp_async16(strip + r * RC + (v << 4), src0 + r * row_pitch + (static_cast<size_t>(v) << 4), true);
+    ptx::cp_async_commit();
+    ptx::cp_async_wait<0>();  // all vectors of a thread in flight at once (a load -> store loop waits per vector)
   } else {
     for (int i = threadIdx.x; i < p * RC; i += blockDim.x) {
       const int r = i / RC;
@@ -397,13 +407,19 @@ cudaError_t launch_resize_t(const uint8_t* in, int n, int sh, int sw, int R, con
                             int p, int Kpad, int rows_in, cudaStream_t stream) {
   const int in_cap = ((rows_in * sw * 3 + 15 + 16 + 48) / 16) * 16;  // staged bytes incl. the alignment head + window slack
   const size_t smem = static_cast<size_t>(in_cap) + static_cast<size_t>(rows_in) * R * 3;
-  cudaError_t e = cudaFuncSetAttribute(preprocess_resize_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e != cudaSuccess) return e;
   dim3 grid((R + TH2 - 1) / TH2, n);
-  preprocess_resize_kernel<OutT><<<grid, 256, smem, stream>>>(in, in + static_cast<size_t>(n) * sh * sw * 3, sh, sw, R, t,
-                                                              static_cast<OutT*>(out), layout, p, Kpad, in_cap, rows_in);
-  return cudaGetLastError();
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 256, smem, stream>>>(in, in + static_cast<size_t>(n) * sh * sw * 3, sh, sw, R, t, static_cast<OutT*>(out), layout, p,
+                                      Kpad, in_cap, rows_in);
+    return cudaGetLastError();
+  };
+  const int taps = t.need_h ? t.h_ksize : 1;
+  if (taps <= 4) return launch(preprocess_resize_kernel<OutT, 4>);
+  if (taps <= 6) return launch(preprocess_resize_kernel<OutT, 6>);
+  if (taps <= 9) return launch(preprocess_resize_kernel<OutT, 9>);
+  return launch(preprocess_resize_kernel<OutT, KMAX>);
 }
 
 }  // namespace
