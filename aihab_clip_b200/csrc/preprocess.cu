@@ -319,6 +319,8 @@ __global__ void __launch_bounds__(256) normalize_im2col16_kernel(const uint8_t* 
                                                                  int top, int left, uint16_t* __restrict__ out, int p_rt) {
   const int p = PS ? PS : p_rt;
   extern __shared__ __align__(16) uint8_t strip[];  // [p][R * 3]
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int gy = blockIdx.x, img = blockIdx.y;
   const int g = R / p, RC = R * 3;
   const uint8_t* src0 = in + ((static_cast<size_t>(img) * sh + top + gy * p) * sw + left) * 3;
@@ -441,14 +443,25 @@ cudaError_t launch_preprocess(const uint8_t* in, int n, int sh, int sw, int R, c
       out_dtype != 0 && p * R * 3 <= 40 * 1024) {
     const dim3 grid(R / p, n);
     const size_t smem = static_cast<size_t>(p) * R * 3;
+    // programmatic dependent launch: the CTAs are scheduled while the previous kernel of the stream drains and wait
+    // (griddepcontrol.wait) before their first global access
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
     auto launch = [&](auto kern) {
-      kern<<<grid, 256, smem, stream>>>(in, sh, sw, R, t.crop_top, t.crop_left, static_cast<uint16_t*>(out), p);
+      return cudaLaunchKernelEx(&cfg, kern, in, sh, sw, R, t.crop_top, t.crop_left, static_cast<uint16_t*>(out), p);
     };
     const bool bf = out_dtype == 2;
-    if (p == 16) bf ? launch(normalize_im2col16_kernel<true, 16>) : launch(normalize_im2col16_kernel<false, 16>);
-    else if (p == 32) bf ? launch(normalize_im2col16_kernel<true, 32>) : launch(normalize_im2col16_kernel<false, 32>);
-    else bf ? launch(normalize_im2col16_kernel<true, 0>) : launch(normalize_im2col16_kernel<false, 0>);
-    return cudaGetLastError();
+    if (p == 16) return bf ? launch(normalize_im2col16_kernel<true, 16>) : launch(normalize_im2col16_kernel<false, 16>);
+    if (p == 32) return bf ? launch(normalize_im2col16_kernel<true, 32>) : launch(normalize_im2col16_kernel<false, 32>);
+    return bf ? launch(normalize_im2col16_kernel<true, 0>) : launch(normalize_im2col16_kernel<false, 0>);
   }
   if (layout == 1 && Kpad > 3 * p * p) {
     const long rows = static_cast<long>(n) * (R / p) * (R / p);
