@@ -379,6 +379,7 @@ struct aihab_vit {
   CUtensorMap m_hring;           // A operand of c_proj over the ring
   // AIHAB_MLP_FUSED=1: c_fc + c_proj as ONE kernel (mlp_fused_kernel) with the same ring / counters; tile lists per M
   bool mlp_fused = false;
+  bool ln_chain = true;  // ln_pre and ln_1 of the first block in one pass (AIHAB_LN_CHAIN=0: two launches)
   struct TileList {
     std::vector<uint32_t> host;
     uint32_t* dev = nullptr;
@@ -501,7 +502,8 @@ int run_gemm(aihab_vit* h, const CUtensorMap& ma, const CUtensorMap (&mw)[2], in
 }
 
 // the residual attention blocks (clip/model.py:165-197) on the M = n * L rows of the fp32 residual stream h->x
-int run_blocks(aihab_vit* h, int n, cudaStream_t s) {
+// ln1_done: ln_1 of the first block is already in h->y2 (fused into the ln_pre pass by run_tower)
+int run_blocks(aihab_vit* h, int n, cudaStream_t s, bool ln1_done = false) {
   const int D = h->D, L = h->L, M = n * L;
   const int layers = static_cast<int>(h->blocks.size());
   int nsb = 0;  // stat blocks per row written by the last residual GEMM
@@ -517,7 +519,7 @@ int run_blocks(aihab_vit* h, int n, cudaStream_t s) {
     aihab_vit::Block& b = h->blocks[l];
     // x = x + out_proj(attn(in_proj(ln_1(x))))   (clip/model.py:181,184)
     if (l == 0 || !h->ln_fold) {
-      {
+      if (!(l == 0 && ln1_done)) {
         ProfScope ps(PC_LN, 6.0 * M * D, s);
         CKL(aihab::launch_layernorm(h->x, D, nullptr, 0, b.ln1_g, b.ln1_b, nullptr, h->y2, h->bf16, M, D, s));
       }
@@ -692,11 +694,16 @@ int run_tower(aihab_vit* h, int n, void* feats_out, int out_dtype, cudaStream_t 
   if (run_gemm(h, h->m_patches, h->m_conv, n * h->g2, D, h->Kpad, aihab::EPI_PATCH_32, nullptr, nullptr, h->x, D, s))
     return 1;
   // class token row + ln_pre, in place on the fp32 residual stream (clip/model.py:220-222)
+  const bool chain = h->ln_chain && !h->blocks.empty();
   {
-    ProfScope ps(PC_LN, 8.0 * M * D, s);
-    CKL(aihab::launch_layernorm(h->x, D, h->cls0, L, h->lnpre_g, h->lnpre_b, h->x, nullptr, 0, M, D, s));
+    ProfScope ps(PC_LN, (chain ? 10.0 : 8.0) * M * D, s);
+    if (chain)  // ... and ln_1 of the first block from the same registers
+      CKL(aihab::launch_layernorm2(h->x, D, h->cls0, L, h->lnpre_g, h->lnpre_b, h->x, h->blocks[0].ln1_g, h->blocks[0].ln1_b,
+                                   h->y2, h->bf16, M, D, s));
+    else
+      CKL(aihab::launch_layernorm(h->x, D, h->cls0, L, h->lnpre_g, h->lnpre_b, h->x, nullptr, 0, M, D, s));
   }
-  if (run_blocks(h, n, s)) return 1;
+  if (run_blocks(h, n, s, chain)) return 1;
   // ln_post on token 0 of every image (clip/model.py:228); rows are L*D apart
   float* o32 = out_dtype == AIHAB_F32 ? static_cast<float*>(feats_out) : nullptr;
   void* o16 = out_dtype == AIHAB_F32 ? nullptr : feats_out;
@@ -768,6 +775,7 @@ int build_stack(aihab_vit* h, int layers, const aihab_vit_block_weights* blocks,
     }
   }
   {
+    if (const char* ec = getenv("AIHAB_LN_CHAIN")) h->ln_chain = ec[0] != '0';
     const char* e = getenv("AIHAB_MLP_PIPE");
     const char* ef = getenv("AIHAB_MLP_FUSED");
     const bool fused = ef != nullptr && ef[0] == '1';

@@ -65,6 +65,64 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
   }
 }
 
+// ln_pre followed by ln_1 of the first block in one pass over the row: y = LN(x; g1, b1) is written as the fp32 residual
+// stream and, still in registers, normalised again (LN(y; g2, b2)) into the 16-bit A operand of the first in_proj GEMM.
+// The second stage is the arithmetic of layernorm_kernel on the values it would have re-read, so the result is
+// bit-identical to the two launches; it saves the launch and one read of the residual stream per step.
+template <int VPL>
+__global__ void __launch_bounds__(128) layernorm2_kernel(const float* __restrict__ x, size_t ldx,
+                                                         const float* __restrict__ cls0, int L,
+                                                         const float* __restrict__ g1, const float* __restrict__ b1,
+                                                         float* out32, const float* __restrict__ g2,
+                                                         const float* __restrict__ b2, void* out16, int out_bf16, int rows) {
+  constexpr int D = VPL * 128;
+  ptx::griddep_launch();
+  ptx::griddep_wait();
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* src = (cls0 != nullptr && (row % L) == 0) ? cls0 : x + static_cast<size_t>(row) * ldx;
+  float4 v[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) v[i] = *reinterpret_cast<const float4*>(src + (i * 32 + lane) * 4);
+#pragma unroll 1
+  for (int stage = 0; stage < 2; ++stage) {
+    const float* gamma = stage ? g2 : g1;
+    const float* beta = stage ? b2 : b1;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (stage == 0) {
+        *reinterpret_cast<float4*>(out32 + static_cast<size_t>(row) * D + col) = y;
+        v[i] = y;
+      } else {
+        uint2 pk;
+        pk.x = out_bf16 ? ptx::pack2<true>(y.x, y.y) : ptx::pack2<false>(y.x, y.y);
+        pk.y = out_bf16 ? ptx::pack2<true>(y.z, y.w) : ptx::pack2<false>(y.z, y.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out16) + static_cast<size_t>(row) * D + col) = pk;
+      }
+    }
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ float load_as_float(const T* p);
 template <>
@@ -287,6 +345,27 @@ cudaError_t launch_layernorm(const float* x, size_t ldx, const float* cls0, int 
     default: return cudaErrorInvalidValue;
   }
 #undef AIHAB_LN
+  return e;
+}
+
+cudaError_t launch_layernorm2(const float* x, size_t ldx, const float* cls0, int L, const float* g1, const float* b1,
+                              float* out32, const float* g2, const float* b2, void* out16, int out_bf16, int rows, int D,
+                              cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (D % 128 != 0 || D > 2048 || (ldx & 3) != 0 || out32 == nullptr || out16 == nullptr) return cudaErrorInvalidValue;
+  const int grid = (rows + 3) / 4;
+  cudaError_t e = cudaSuccess;
+#define AIHAB_LN2(V)                                                                                              \
+  case V:                                                                                                         \
+    e = launch_kernel(layernorm2_kernel<V>, grid, 128, 0, stream, 1, true, x, ldx, cls0, L > 0 ? L : 1, g1, b1, out32, \
+                      g2, b2, out16, out_bf16, rows);                                                               \
+    break;
+  switch (D / 128) {
+    AIHAB_LN2(1) AIHAB_LN2(2) AIHAB_LN2(3) AIHAB_LN2(4) AIHAB_LN2(5) AIHAB_LN2(6) AIHAB_LN2(7) AIHAB_LN2(8)
+    AIHAB_LN2(9) AIHAB_LN2(10) AIHAB_LN2(11) AIHAB_LN2(12) AIHAB_LN2(13) AIHAB_LN2(14) AIHAB_LN2(15) AIHAB_LN2(16)
+    default: return cudaErrorInvalidValue;
+  }
+#undef AIHAB_LN2
   return e;
 }
 

@@ -17,6 +17,12 @@ cudaError_t launch_layernorm(const float* x, size_t ldx, const float* cls0, int 
                              const float* beta, float* out32, void* out16, int out_bf16, int rows, int D,
                              cudaStream_t stream);
 
+// Two chained LayerNorms in one pass (ln_pre -> ln_1 of the first block, clip/model.py:222,181): out32 = LN(x; g1, b1) (may
+// alias x), out16 = LN(out32; g2, b2); bit-identical to two launch_layernorm calls.
+cudaError_t launch_layernorm2(const float* x, size_t ldx, const float* cls0, int L, const float* g1, const float* b1,
+                              float* out32, const float* g2, const float* b2, void* out16, int out_bf16, int rows, int D,
+                              cudaStream_t stream);
+
 // im2col for the stride-p patch embedding (clip/model.py:204,217): images [N,3,R,R] -> rows [N*g*g, Kpad]
 // 16-bit with column order (c, ky, kx) matching conv1.weight.reshape(D, 3*p*p); columns >= 3*p*p are zero.
 //   in_dtype: 0 = fp32, 1 = fp16, 2 = bf16

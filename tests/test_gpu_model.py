@@ -330,6 +330,21 @@ def test_sharded_extractor_host_copy_is_complete_on_return(tmp_path, cuda_device
     assert torch.equal(host[:, :E], res["features"].cpu())   # the clone taken after run() 1 is unaffected
 
 
+def test_chained_layernorm_is_bit_identical(tmp_path, cuda_device, monkeypatch):
+    """ln_pre and ln_1 of the first block run as ONE pass over the residual rows (layernorm2_kernel); the second stage is
+    the arithmetic of the standalone kernel on the values it would have re-read: same features bit for bit."""
+    geom = GEOMETRIES["ViT-tiny/16"]
+    u8 = torch.from_numpy(synthetic_images_u8(37, geom.image_resolution)).to(cuda_device)
+    out = {}
+    for chain in ("0", "1"):
+        monkeypatch.setenv("AIHAB_LN_CHAIN", chain)
+        _, model, _ = load_model(tmp_path, geom.name, 1, cuda_device)
+        model.float()
+        out[chain] = model.encode_image_u8(u8)
+        del model
+    assert torch.isfinite(out["1"]).all() and torch.equal(out["0"], out["1"])
+
+
 @pytest.mark.parametrize("mode,ring_pairs", [("AIHAB_MLP_PIPE", None), ("AIHAB_MLP_FUSED", None), ("AIHAB_MLP_FUSED", "6")])
 def test_pipelined_mlp_is_bit_identical(tmp_path, cuda_device, monkeypatch, mode, ring_pairs):
     """AIHAB_MLP_PIPE=1: c_fc and c_proj run concurrently on half of the SMs each and hand the hidden activations over
